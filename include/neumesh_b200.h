@@ -1,0 +1,143 @@
+/*
+ * neumesh_b200 - C ABI of the B200-native NeuMesh rendering hot path.
+ *
+ * The reference (zju3dv/NeuMesh) is pure Python: it has no FFI of its own.  Its only native code on this path is
+ * the third-party `frnn` extension, reached through `frnn.frnn_grid_points` at models/mesh_grid.py:64 and :109.
+ * Every entry point below names the reference Python interface it replaces (file:line relative to the reference
+ * tree) - a maintainer binds them with ctypes (neumesh_b200/_lib.py is that binding).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / C++ types.
+ *   - every pointer is a DEVICE pointer (fp32 unless stated), caller-owned, dense row-major.
+ *   - every call takes the CUDA stream to enqueue on (`void*` = cudaStream_t); calls are asynchronous with
+ *     respect to the host unless stated; handles are immutable after creation and may be shared by streams.
+ *   - return value: 0 on success, non-zero on failure; `nmb_last_error()` returns a thread-local message.
+ *   - nothing here falls back to the CPU: without a CUDA device every call fails.
+ */
+#ifndef NEUMESH_B200_H_
+#define NEUMESH_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMB_VERSION 100
+
+typedef struct nmb_grid nmb_grid;   /* spatial index over mesh vertices (replaces the FRNN `grid` tuple) */
+typedef struct nmb_field nmb_field; /* packed NeuMesh field: vertex tables + both MLPs */
+
+/* last error message of the calling thread ("" if none) */
+const char* nmb_last_error(void);
+/* library version (NMB_VERSION) - also the "does the extension load" probe */
+int nmb_version(void);
+/* number of kernels this library has launched in the calling process since load (bench.py: gpu_launches) */
+int64_t nmb_launch_count(void);
+
+/* ---- spatial index ------------------------------------------------------------------------------------------
+ * Replaces the cached grid built by MeshGrid.__init__ (models/mesh_grid.py:64-74: a V x V, K=32 FRNN self-query
+ * whose only kept result is the `grid` tuple).  Builds a Morton-ordered sparse octree with tight node boxes.
+ * Synchronises the stream (build is a one-off per mesh). */
+int nmb_grid_create(const float* vertices /*[V,3]*/, int64_t V, void* stream, nmb_grid** out);
+void nmb_grid_destroy(nmb_grid* g);
+int64_t nmb_grid_num_vertices(const nmb_grid* g);
+/* sorted slot -> original vertex index, int32 [V] (device pointer owned by the grid) */
+const int32_t* nmb_grid_order(const nmb_grid* g);
+
+/* Exact K-nearest neighbours: frnn.frnn_grid_points(points1=xyz, points2=vertices, K, r, grid, return_sorted=True)
+ * as called at models/mesh_grid.py:109-119.  d2 [M,K] squared distances ascending, idx [M,K] int64 indices in the
+ * ORIGINAL vertex order; entries farther than r are set to -1 (FRNN's padding).  1 <= K <= 32. */
+int nmb_knn(const nmb_grid* g, const float* xyz /*[M,3]*/, int64_t M, int K, float r, float* d2, int64_t* idx,
+            void* stream);
+
+/* MeshGrid.compute_distance_frnn (models/mesh_grid.py:88-144) with K = 8: inverse-distance weights and the
+ * indicator-blended signed distance.  ds [M], idx [M,8] int64 (original order), w [M,8];
+ * grad_ds [M,3] = d ds / d xyz with idx, w held constant (nullable). */
+int nmb_mesh_distance(const nmb_grid* g, const float* indicator /*[V,3] original order*/, float indicator_weight,
+                      const float* xyz /*[M,3]*/, int64_t M, float* ds, int64_t* idx, float* w, float* grad_ds,
+                      void* stream);
+
+/* ---- field ---------------------------------------------------------------------------------------------------
+ * NeuMesh parameters (models/frameworks/neumesh/neumesh.py:43-102) in the reference's state_dict layout.
+ * Weight-norm layers are passed as (v, g, bias); the library folds W = g * v / ||v||_row. */
+typedef struct nmb_field_desc {
+  int32_t D_density;          /* hidden layers of the geometry MLP (reference default 3) */
+  int32_t D_color;            /* hidden layers of the colour MLP (4) */
+  int32_t W;                  /* hidden width (256) */
+  int32_t geometry_dim;       /* Fg (32) */
+  int32_t color_dim;          /* Fc (32) */
+  int32_t multires_d;         /* 8 */
+  int32_t multires_fg;        /* 2 */
+  int32_t multires_ft;        /* 2 */
+  int32_t multires_view;      /* 4 */
+  int32_t enable_nablas_input;
+  float indicator_weight;     /* sigmoid(indicator_weight_raw) or 0.1 (neumesh.py:262-269) */
+  float s;                    /* forward_s() = exp(ln_s * speed_factor) (neumesh.py:170-171) */
+  const float* geometry_features; /* [V,Fg] */
+  const float* color_features;    /* [V,Fc] */
+  const float* indicator_vector;  /* [V,3]  */
+  const float* geo_v[8];      /* pts_linears.*.weight_v, then density_linear.weight_v: [out,in] */
+  const float* geo_g[8];      /* ...weight_g [out,1] */
+  const float* geo_b[8];      /* ...bias [out] */
+  const float* col_w[8];      /* views_linears.*.weight, then color_linear.0.weight */
+  const float* col_b[8];
+} nmb_field_desc;
+
+/* mlp_engine: 0 = tcgen05 3xTF32 tensor-core MLP (default), 1 = fp32 FFMA MLP (verification path) */
+int nmb_field_create(const nmb_grid* g, const nmb_field_desc* desc, int mlp_engine, void* stream, nmb_field** out);
+void nmb_field_destroy(nmb_field* f);
+/* re-pack after the caller changed parameter values in place (same shapes) */
+int nmb_field_update(nmb_field* f, const nmb_field_desc* desc, void* stream);
+
+/* NeuMesh.forward_density_only / forward_with_nablas (neumesh.py:140-154): sdf [M]; nabla [M,3] nullable. */
+int nmb_field_sdf(const nmb_field* f, const float* xyz /*[M,3]*/, int64_t M, float* sdf, float* nabla, void* stream);
+/* NeuMesh.forward (neumesh.py:113-138, need_nablas=True): sdf [M], rgb [M,3], nabla [M,3] nullable. */
+int nmb_field_forward(const nmb_field* f, const float* xyz, const float* view_dirs, int64_t M, float* sdf,
+                      float* rgb, float* nabla, void* stream);
+
+/* ---- renderer ------------------------------------------------------------------------------------------------
+ * volume_render (models/renderer.py:105-368), un-batched, perturb=False, no grad. */
+typedef struct nmb_render_cfg {
+  float obj_bounding_radius;  /* 1.0 */
+  int32_t N_samples;          /* 64 */
+  int32_t N_importance;       /* 64 */
+  int32_t N_upsample_iters;   /* 4 */
+  int32_t bounded_near_far;   /* 1 */
+  int32_t calc_normal;
+  int32_t white_bkgd;
+  int32_t use_near_bypass;
+  float near_bypass;
+  int32_t use_far_bypass;
+  float far_bypass;
+  int32_t normalize_dirs;     /* 1: apply F.normalize to rays_d (renderer.py:153) */
+} nmb_render_cfg;
+
+/* optional per-sample outputs (renderer.py:335-348, detailed_output=True); any pointer may be NULL.
+ * P = N_samples + N_importance. */
+typedef struct nmb_render_detail {
+  float* d_all;              /* [N,P]   sorted sample depths */
+  float* implicit_surface;   /* [N,P]   sdf at the samples */
+  float* implicit_nablas;    /* [N,P,3] (calc_normal only) */
+  float* radiance;           /* [N,P-1,3] */
+  float* sdf_mid;            /* [N,P-1] sdf at the mid-points ("density" of samples_output) */
+  float* near_far;           /* [N,2] */
+} nmb_render_detail;
+
+/* bytes of scratch needed for `max_rays_per_chunk` rays */
+int64_t nmb_render_workspace_bytes(const nmb_render_cfg* cfg, int64_t rays_per_chunk);
+/* rgb [N,3], depth [N], acc [N], normals [N,3] (nullable unless calc_normal). workspace: device scratch of at
+ * least nmb_render_workspace_bytes(cfg, rays_per_chunk) bytes. */
+int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_o, const float* rays_d, int64_t N,
+               int64_t rays_per_chunk, float* rgb, float* depth, float* acc, float* normals,
+               const nmb_render_detail* detail, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Ray generation (utils/rend_util.py:97-176 get_rays/lift, full image, no skew handling beyond K[0,1]).
+ * c2w [3,4] or [4,4] row-major (first 3 rows used), intr = {fx, fy, cx, cy, skew}. rays_o, rays_d [H*W,3]. */
+int nmb_get_rays(const float* c2w_host /*HOST 12 floats*/, const float* intr_host /*HOST 5 floats*/, int32_t H,
+                 int32_t W, float* rays_o, float* rays_d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEUMESH_B200_H_ */

@@ -1,0 +1,64 @@
+// Shared helpers for the neumesh_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace nmb {
+
+void set_error(const std::string& msg);
+void count_launch(int n = 1);
+
+#define NMB_CUDA_OK(expr)                                                                               \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      ::nmb::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ +  \
+                       ":" + std::to_string(__LINE__) + ")");                                           \
+      return 1;                                                                                         \
+    }                                                                                                   \
+  } while (0)
+
+#define NMB_CHECK(cond, msg)                                                \
+  do {                                                                      \
+    if (!(cond)) {                                                          \
+      ::nmb::set_error(std::string(msg) + " [" #cond "]");                  \
+      return 2;                                                             \
+    }                                                                       \
+  } while (0)
+
+#define NMB_LAUNCH_OK()                                      \
+  do {                                                       \
+    ::nmb::count_launch();                                   \
+    NMB_CUDA_OK(cudaGetLastError());                         \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t align_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+// Simple owning device buffer (build-time allocations; hot-path scratch comes from the caller's workspace).
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  int64_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  cudaError_t alloc(int64_t count) {
+    release();
+    n = count;
+    if (count <= 0) return cudaSuccess;
+    return cudaMalloc(reinterpret_cast<void**>(&p), sizeof(T) * static_cast<size_t>(count));
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+};
+
+int sm_count();
+
+}  // namespace nmb

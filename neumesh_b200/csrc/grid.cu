@@ -1,0 +1,720 @@
+// Spatial index over the mesh vertices and the exact 8-NN + mesh-distance kernels.
+//
+// Replaces the reference's use of the third-party FRNN package:
+//   models/mesh_grid.py:64-74   grid construction (a V x V, K=32 self-query whose only kept result is `grid`)
+//   models/mesh_grid.py:109-119 K=8 query  (r = 100 never binds => exact KNN, squared distances ascending)
+//   models/mesh_grid.py:121-144 inverse-distance weights + indicator-blended signed distance
+//
+// B200-first design.  FRNN's uniform grid degenerates to one cell at r=100 (cell = r/2) and brute-forces all V
+// vertices per query.  Here the vertices are Morton-sorted once and indexed by a sparse octree whose nodes carry
+// TIGHT boxes; a query walks it depth-first, nearest child first, pruning against its current 8th-best distance.
+// That is exact for any query position (the renderer probes the whole unit-sphere chord, far from the surface),
+// needs no radius, and touches ~100-300 B of L2-resident nodes/points per level instead of 12*V bytes.
+// One thread per query; a warp holds 32 neighbouring rays at the same sample index, so the walks are coherent and
+// node/point loads are mostly L1 hits.  Distances use un-fused fp32 mul/add so that neighbour selection is
+// bit-identical to an IEEE fp32 brute force (the oracle).
+#include <cub/cub.cuh>
+#include <math_constants.h>
+
+#include <vector>
+
+#include "grid.cuh"
+
+namespace nmb {
+
+// ------------------------------------------------------------------------------------------------------------
+// build
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t expand_bits10(uint32_t v) {
+  v = (v * 0x00010001u) & 0xFF0000FFu;
+  v = (v * 0x00000101u) & 0x0F00F00Fu;
+  v = (v * 0x00000011u) & 0xC30C30C3u;
+  v = (v * 0x00000005u) & 0x49249249u;
+  return v;
+}
+
+__global__ void bbox_kernel(const float* __restrict__ v, int64_t V, float* __restrict__ out /*6: min xyz, max xyz*/) {
+  float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F};
+  float hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < V; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float x = v[i * 3 + c];
+      lo[c] = fminf(lo[c], x);
+      hi[c] = fmaxf(hi[c], x);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+      hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    // ordered-int trick: works for any sign
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      int a = __float_as_int(lo[c]);
+      a = a >= 0 ? a : a ^ 0x7fffffff;
+      atomicMin(reinterpret_cast<int*>(out) + c, a);
+      int b = __float_as_int(hi[c]);
+      b = b >= 0 ? b : b ^ 0x7fffffff;
+      atomicMax(reinterpret_cast<int*>(out) + 3 + c, b);
+    }
+  }
+}
+
+__global__ void morton_kernel(const float* __restrict__ v, int64_t V, float3 bmin, float inv_cell, int levels,
+                              uint32_t* __restrict__ code, int32_t* __restrict__ iota) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  const uint32_t maxc = (1u << levels) - 1u;
+  uint32_t q[3];
+  const float b[3] = {bmin.x, bmin.y, bmin.z};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float t = (v[i * 3 + c] - b[c]) * inv_cell;
+    int qi = (int)floorf(t);
+    q[c] = (uint32_t)min(max(qi, 0), (int)maxc);
+  }
+  code[i] = (expand_bits10(q[0]) << 2) | (expand_bits10(q[1]) << 1) | expand_bits10(q[2]);
+  iota[i] = (int32_t)i;
+}
+
+__global__ void gather_points_kernel(const float* __restrict__ v, const int32_t* __restrict__ order, int64_t V,
+                                     float4* __restrict__ pts, int32_t* __restrict__ inv) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  int32_t o = order[i];
+  pts[i] = make_float4(v[(int64_t)o * 3 + 0], v[(int64_t)o * 3 + 1], v[(int64_t)o * 3 + 2], __int_as_float(o));
+  inv[o] = (int32_t)i;
+}
+
+// level build: see DESIGN.md "octree build".  pnode[i] = id of the still-subdividing node holding point i, or -1.
+__global__ void lvl_heads_kernel(const uint32_t* __restrict__ code, const int32_t* __restrict__ pnode, int64_t V,
+                                 int shift, int32_t* __restrict__ head) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  int32_t p = pnode[i];
+  int h = 0;
+  if (p >= 0) h = (i == 0) || (pnode[i - 1] != p) || ((code[i] >> shift) != (code[i - 1] >> shift));
+  head[i] = h;
+}
+
+__global__ void lvl_create_kernel(const uint32_t* __restrict__ code, const int32_t* __restrict__ pnode,
+                                  const int32_t* __restrict__ head, const int32_t* __restrict__ cid_excl, int64_t V,
+                                  int shift, int32_t lvl_off, int32_t* __restrict__ nbegin, int32_t* __restrict__ nend,
+                                  int32_t* __restrict__ nfirst, int32_t* __restrict__ nlast,
+                                  int32_t* __restrict__ newnode) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  int32_t p = pnode[i];
+  if (p < 0) {
+    newnode[i] = -1;
+    return;
+  }
+  int32_t gid = lvl_off + cid_excl[i] + head[i] - 1;
+  newnode[i] = gid;
+  if (head[i]) {
+    nbegin[gid] = (int32_t)i;
+    nfirst[gid] = -1;
+    nlast[gid] = -1;
+  }
+  bool last = (i + 1 == V) || (pnode[i + 1] != p) || ((code[i + 1] >> shift) != (code[i] >> shift));
+  if (last) nend[gid] = (int32_t)(i + 1);
+  if ((int32_t)i == nbegin[p]) nfirst[p] = gid;
+  if ((int32_t)(i + 1) == nend[p]) nlast[p] = gid;
+}
+
+__global__ void lvl_activate_kernel(const int32_t* __restrict__ newnode, const int32_t* __restrict__ nbegin,
+                                    const int32_t* __restrict__ nend, int64_t V, int can_split,
+                                    int32_t* __restrict__ pnode) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  int32_t g = newnode[i];
+  int32_t r = -1;
+  if (g >= 0 && can_split && (nend[g] - nbegin[g]) > LEAF_MAX) r = g;
+  pnode[i] = r;
+}
+
+__global__ void lvl_boxes_kernel(int32_t first_node, int32_t n_nodes, const int32_t* __restrict__ nbegin,
+                                 const int32_t* __restrict__ nend, const int32_t* __restrict__ nfirst,
+                                 const int32_t* __restrict__ nlast, const float4* __restrict__ pts,
+                                 float4* __restrict__ nodes) {
+  int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_nodes) return;
+  int32_t n = first_node + t;
+  float3 lo = make_float3(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F);
+  float3 hi = make_float3(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+  int32_t fc = nfirst[n];
+  float link, cnt;
+  if (fc < 0) {  // leaf: box of its points
+    int32_t b = nbegin[n], e = nend[n];
+    for (int32_t i = b; i < e; ++i) {
+      float4 p = pts[i];
+      lo.x = fminf(lo.x, p.x); lo.y = fminf(lo.y, p.y); lo.z = fminf(lo.z, p.z);
+      hi.x = fmaxf(hi.x, p.x); hi.y = fmaxf(hi.y, p.y); hi.z = fmaxf(hi.z, p.z);
+    }
+    link = __int_as_float(b);
+    cnt = __int_as_float(-(e - b));
+  } else {  // internal: union of the (already final) child boxes
+    int32_t lc = nlast[n];
+    for (int32_t c = fc; c <= lc; ++c) {
+      float4 a = nodes[2 * c], b = nodes[2 * c + 1];
+      lo.x = fminf(lo.x, a.x); lo.y = fminf(lo.y, a.y); lo.z = fminf(lo.z, a.z);
+      hi.x = fmaxf(hi.x, b.x); hi.y = fmaxf(hi.y, b.y); hi.z = fmaxf(hi.z, b.z);
+    }
+    link = __int_as_float(fc);
+    cnt = __int_as_float(lc - fc + 1);
+  }
+  nodes[2 * n] = make_float4(lo.x, lo.y, lo.z, link);
+  nodes[2 * n + 1] = make_float4(hi.x, hi.y, hi.z, cnt);
+}
+
+static int build_grid(const float* vertices, int64_t V, cudaStream_t stream, nmb_grid* g) {
+  NMB_CHECK(V >= KNN_K, "mesh needs at least 8 vertices");
+  NMB_CHECK(V < (int64_t(1) << 30), "too many vertices");
+  g->V = V;
+  const int threads = 256;
+  const int64_t blocks = ceil_div(V, threads);
+
+  // bounding cube
+  DevBuf<float> bb;
+  NMB_CUDA_OK(bb.alloc(6));
+  {
+    int init[6] = {0x7f7fffff, 0x7f7fffff, 0x7f7fffff, (int)0x80800000, (int)0x80800000, (int)0x80800000};
+    // ordered-int encodings of +FLT_MAX / -FLT_MAX
+    init[3] = init[4] = init[5] = (int)(0xff7fffffu ^ 0x7fffffffu);
+    NMB_CUDA_OK(cudaMemcpyAsync(bb.p, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+    bbox_kernel<<<(unsigned)(blocks < 1024 ? blocks : 1024), threads, 0, stream>>>(vertices, V, bb.p);
+    NMB_LAUNCH_OK();
+    int raw[6];
+    NMB_CUDA_OK(cudaMemcpyAsync(raw, bb.p, sizeof(raw), cudaMemcpyDeviceToHost, stream));
+    NMB_CUDA_OK(cudaStreamSynchronize(stream));
+    float lo[3], hi[3];
+    for (int c = 0; c < 3; ++c) {
+      int a = raw[c];
+      a = a >= 0 ? a : a ^ 0x7fffffff;
+      int b = raw[3 + c];
+      b = b >= 0 ? b : b ^ 0x7fffffff;
+      memcpy(&lo[c], &a, 4);
+      memcpy(&hi[c], &b, 4);
+    }
+    float side = 0.f;
+    for (int c = 0; c < 3; ++c) side = fmaxf(side, hi[c] - lo[c]);
+    NMB_CHECK(side == side && side < 1e30f, "non-finite vertex coordinates");
+    side = side * 1.0001f + 1e-6f;
+    for (int c = 0; c < 3; ++c) g->bmin[c] = lo[c];
+    // depth: aim at ~2-4 points per finest cell for a surface-like point set (#cells ~ 4^L)
+    int L = 1;
+    while (L < 10 && (double)V / pow(4.0, L) > 2.0) ++L;
+    g->levels = L;
+    g->inv_cell = (float)(1u << L) / side;
+  }
+  const int L = g->levels;
+
+  // Morton sort
+  DevBuf<uint32_t> code_in, code;
+  DevBuf<int32_t> iota;
+  NMB_CUDA_OK(code_in.alloc(V));
+  NMB_CUDA_OK(code.alloc(V));
+  NMB_CUDA_OK(iota.alloc(V));
+  NMB_CUDA_OK(g->order.alloc(V));
+  NMB_CUDA_OK(g->inv.alloc(V));
+  NMB_CUDA_OK(g->pts.alloc(V));
+  morton_kernel<<<(unsigned)blocks, threads, 0, stream>>>(vertices, V, make_float3(g->bmin[0], g->bmin[1], g->bmin[2]),
+                                                          g->inv_cell, L, code_in.p, iota.p);
+  NMB_LAUNCH_OK();
+  {
+    size_t tmp_bytes = 0;
+    NMB_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, code_in.p, code.p, iota.p, g->order.p, (int)V, 0,
+                                                3 * L, stream));
+    DevBuf<char> tmp;
+    NMB_CUDA_OK(tmp.alloc((int64_t)tmp_bytes));
+    NMB_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, code_in.p, code.p, iota.p, g->order.p, (int)V, 0,
+                                                3 * L, stream));
+    count_launch(4);
+    NMB_CUDA_OK(cudaStreamSynchronize(stream));
+  }
+  gather_points_kernel<<<(unsigned)blocks, threads, 0, stream>>>(vertices, g->order.p, V, g->pts.p, g->inv.p);
+  NMB_LAUNCH_OK();
+
+  // level-by-level subdivision
+  const int64_t cap = V + (int64_t)(L + 1) * (V / (LEAF_MAX + 1) + 1) + 16;
+  DevBuf<int32_t> nbegin, nend, nfirst, nlast, pnode, newnode, head, cid;
+  NMB_CUDA_OK(nbegin.alloc(cap));
+  NMB_CUDA_OK(nend.alloc(cap));
+  NMB_CUDA_OK(nfirst.alloc(cap));
+  NMB_CUDA_OK(nlast.alloc(cap));
+  NMB_CUDA_OK(pnode.alloc(V));
+  NMB_CUDA_OK(newnode.alloc(V));
+  NMB_CUDA_OK(head.alloc(V));
+  NMB_CUDA_OK(cid.alloc(V + 1));
+  size_t scan_bytes = 0;
+  NMB_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, head.p, cid.p, (int)V, stream));
+  DevBuf<char> scan_tmp;
+  NMB_CUDA_OK(scan_tmp.alloc((int64_t)scan_bytes));
+
+  std::vector<int32_t> lvl_off;  // first node id of each level
+  lvl_off.push_back(0);
+  {
+    int32_t root[4] = {0, (int32_t)V, -1, -1};
+    NMB_CUDA_OK(cudaMemcpyAsync(nbegin.p, &root[0], 4, cudaMemcpyHostToDevice, stream));
+    NMB_CUDA_OK(cudaMemcpyAsync(nend.p, &root[1], 4, cudaMemcpyHostToDevice, stream));
+    NMB_CUDA_OK(cudaMemcpyAsync(nfirst.p, &root[2], 4, cudaMemcpyHostToDevice, stream));
+    NMB_CUDA_OK(cudaMemcpyAsync(nlast.p, &root[3], 4, cudaMemcpyHostToDevice, stream));
+    // all points start in the root (V >= 8 > ... root splits iff V > LEAF_MAX and L > 0)
+    int fill = (V > LEAF_MAX && L > 0) ? 0 : -1;
+    NMB_CUDA_OK(cudaMemsetAsync(pnode.p, fill == 0 ? 0 : 0xff, sizeof(int32_t) * V, stream));
+  }
+  int32_t n_nodes = 1;
+  lvl_off.push_back(1);
+  for (int l = 0; l < L; ++l) {
+    const int shift = 3 * (L - (l + 1));
+    lvl_heads_kernel<<<(unsigned)blocks, threads, 0, stream>>>(code.p, pnode.p, V, shift, head.p);
+    NMB_LAUNCH_OK();
+    NMB_CUDA_OK(cub::DeviceScan::ExclusiveSum(scan_tmp.p, scan_bytes, head.p, cid.p, (int)V, stream));
+    count_launch(2);
+    int32_t last_cid = 0, last_head = 0;
+    NMB_CUDA_OK(cudaMemcpyAsync(&last_cid, cid.p + (V - 1), 4, cudaMemcpyDeviceToHost, stream));
+    NMB_CUDA_OK(cudaMemcpyAsync(&last_head, head.p + (V - 1), 4, cudaMemcpyDeviceToHost, stream));
+    NMB_CUDA_OK(cudaStreamSynchronize(stream));
+    const int32_t n_new = last_cid + last_head;
+    if (n_new == 0) break;
+    NMB_CHECK((int64_t)n_nodes + n_new <= cap, "octree node capacity exceeded");
+    lvl_create_kernel<<<(unsigned)blocks, threads, 0, stream>>>(code.p, pnode.p, head.p, cid.p, V, shift, n_nodes,
+                                                                 nbegin.p, nend.p, nfirst.p, nlast.p, newnode.p);
+    NMB_LAUNCH_OK();
+    lvl_activate_kernel<<<(unsigned)blocks, threads, 0, stream>>>(newnode.p, nbegin.p, nend.p, V, (l + 1 < L) ? 1 : 0,
+                                                                   pnode.p);
+    NMB_LAUNCH_OK();
+    n_nodes += n_new;
+    lvl_off.push_back(n_nodes);
+  }
+  g->num_nodes = n_nodes;
+  NMB_CUDA_OK(g->nodes.alloc(2 * (int64_t)n_nodes));
+  for (int l = (int)lvl_off.size() - 2; l >= 0; --l) {
+    const int32_t first = lvl_off[l], cnt = lvl_off[l + 1] - lvl_off[l];
+    if (cnt <= 0) continue;
+    lvl_boxes_kernel<<<(unsigned)ceil_div(cnt, threads), threads, 0, stream>>>(first, cnt, nbegin.p, nend.p, nfirst.p,
+                                                                               nlast.p, g->pts.p, g->nodes.p);
+    NMB_LAUNCH_OK();
+  }
+  NMB_CUDA_OK(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// traversal
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sq_dist_rn(float qx, float qy, float qz, float px, float py, float pz) {
+  // (dx*dx + dy*dy) + dz*dz with every operation individually rounded: no FMA contraction
+  const float dx = __fsub_rn(qx, px), dy = __fsub_rn(qy, py), dz = __fsub_rn(qz, pz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ float box_dist_rn(float qx, float qy, float qz, const float4& lo, const float4& hi) {
+  // lower bound of sq_dist_rn over every point inside the box (rounding is monotone)
+  const float dx = fmaxf(fmaxf(__fsub_rn(lo.x, qx), __fsub_rn(qx, hi.x)), 0.f);
+  const float dy = fmaxf(fmaxf(__fsub_rn(lo.y, qy), __fsub_rn(qy, hi.y)), 0.f);
+  const float dz = fmaxf(fmaxf(__fsub_rn(lo.z, qz), __fsub_rn(qz, hi.z)), 0.f);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// Insert (nd, ni) into the ascending list d[0..K-1] (precondition nd < d[K-1]); branch-free, strict '<' keeps
+// the earlier candidate on exact ties.
+template <int K>
+__device__ __forceinline__ void topk_insert(float (&d)[K], int32_t (&ix)[K], float nd, int32_t ni) {
+#pragma unroll
+  for (int k = K - 1; k > 0; --k) {
+    const bool from_above = nd < d[k - 1];  // old d[k-1] (slots above k are still untouched)
+    const bool here = nd < d[k];            // old d[k]
+    const float dk = from_above ? d[k - 1] : (here ? nd : d[k]);
+    const int32_t ik = from_above ? ix[k - 1] : (here ? ni : ix[k]);
+    d[k] = dk;
+    ix[k] = ik;
+  }
+  if (nd < d[0]) {
+    d[0] = nd;
+    ix[0] = ni;
+  }
+}
+
+#define NMB_CSWAP(a, b)                                   \
+  {                                                       \
+    const bool s_ = cd[a] < cd[b];                        \
+    const float t_ = s_ ? cd[a] : cd[b];                  \
+    const int32_t u_ = s_ ? cn[a] : cn[b];                \
+    cd[a] = s_ ? cd[b] : cd[a];                           \
+    cn[a] = s_ ? cn[b] : cn[a];                           \
+    cd[b] = t_;                                           \
+    cn[b] = u_;                                           \
+  }
+
+// Depth-first, nearest-child-first walk.  On return d[]/ix[] hold the K nearest points (ascending squared
+// distance; ix = slot in the Morton-sorted point array).
+template <int K>
+__device__ __forceinline__ void knn_walk(const float4* __restrict__ nodes, const float4* __restrict__ pts, float qx,
+                                         float qy, float qz, float (&d)[K], int32_t (&ix)[K]) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    d[k] = CUDART_INF_F;
+    ix[k] = 0;
+  }
+  int32_t sn[STACK_MAX];
+  float sd[STACK_MAX];
+  int sp = 0;
+  sn[0] = 0;
+  sd[0] = 0.f;
+  sp = 1;
+  while (sp > 0) {
+    --sp;
+    const int32_t n = sn[sp];
+    if (sd[sp] >= d[K - 1]) continue;
+    const float4 a = __ldg(&nodes[2 * n]);
+    const float4 b = __ldg(&nodes[2 * n + 1]);
+    const int32_t link = __float_as_int(a.w);
+    const int32_t cnt = __float_as_int(b.w);
+    if (cnt < 0) {
+      const int32_t e = link - cnt;
+      for (int32_t i = link; i < e; ++i) {
+        const float4 p = __ldg(&pts[i]);
+        const float dd = sq_dist_rn(qx, qy, qz, p.x, p.y, p.z);
+        if (dd < d[K - 1]) topk_insert<K>(d, ix, dd, i);
+      }
+    } else {
+      float cd[8];
+      int32_t cn[8];
+      const float worst = d[K - 1];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        cd[c] = CUDART_INF_F;
+        cn[c] = link + c;
+        if (c < cnt) {
+          const float4 lo = __ldg(&nodes[2 * (link + c)]);
+          const float4 hi = __ldg(&nodes[2 * (link + c) + 1]);
+          const float bd = box_dist_rn(qx, qy, qz, lo, hi);
+          cd[c] = bd < worst ? bd : CUDART_INF_F;
+        }
+      }
+      // 19-comparator sorting network, DESCENDING (largest first) so that the nearest child is pushed last
+      NMB_CSWAP(0, 1) NMB_CSWAP(2, 3) NMB_CSWAP(4, 5) NMB_CSWAP(6, 7)
+      NMB_CSWAP(0, 2) NMB_CSWAP(1, 3) NMB_CSWAP(4, 6) NMB_CSWAP(5, 7)
+      NMB_CSWAP(1, 2) NMB_CSWAP(5, 6) NMB_CSWAP(0, 4) NMB_CSWAP(3, 7)
+      NMB_CSWAP(1, 5) NMB_CSWAP(2, 6)
+      NMB_CSWAP(1, 4) NMB_CSWAP(3, 6)
+      NMB_CSWAP(2, 4) NMB_CSWAP(3, 5)
+      NMB_CSWAP(3, 4)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (cd[c] < CUDART_INF_F && sp < STACK_MAX) {
+          sn[sp] = cn[c];
+          sd[sp] = cd[c];
+          ++sp;
+        }
+      }
+    }
+  }
+}
+#undef NMB_CSWAP
+
+__device__ __forceinline__ void load_query(const PointSrc& src, int64_t p, float& qx, float& qy, float& qz) {
+  if (src.xyz) {
+    qx = src.xyz[p * 3 + 0];
+    qy = src.xyz[p * 3 + 1];
+    qz = src.xyz[p * 3 + 2];
+  } else {
+    const int64_t r = p % src.R;
+    const float z = src.z[p];
+    // pts = rays_o + z * rays_d (renderer.py:85,202,248,264,267): separate mul and add as in torch
+    qx = __fadd_rn(src.rays_o[r * 3 + 0], __fmul_rn(z, src.rays_d[r * 3 + 0]));
+    qy = __fadd_rn(src.rays_o[r * 3 + 1], __fmul_rn(z, src.rays_d[r * 3 + 1]));
+    qz = __fadd_rn(src.rays_o[r * 3 + 2], __fmul_rn(z, src.rays_d[r * 3 + 2]));
+  }
+}
+
+// mesh_grid.py:121-144 for one query whose neighbours are known.
+__device__ __forceinline__ void mesh_distance_point(const float4* __restrict__ pts,
+                                                    const float4* __restrict__ indicator, float w1, float qx,
+                                                    float qy, float qz, const float (&d2)[KNN_K],
+                                                    const int32_t (&ix)[KNN_K], float (&w)[KNN_K], float& ds,
+                                                    float (&grad)[3]) {
+  float wsum = 0.f;
+#pragma unroll
+  for (int k = 0; k < KNN_K; ++k) {
+    w[k] = __fdiv_rn(1.0f, __fadd_rn(__fsqrt_rn(d2[k]), 1e-7f));  // :123-124
+    wsum = __fadd_rn(wsum, w[k]);
+  }
+  ds = 0.f;
+  grad[0] = grad[1] = grad[2] = 0.f;
+#pragma unroll
+  for (int k = 0; k < KNN_K; ++k) {
+    w[k] = __fdiv_rn(w[k], wsum);  // :125
+    const float4 p = __ldg(&pts[ix[k]]);
+    const float4 nv = __ldg(&indicator[ix[k]]);
+    const float vx = __fsub_rn(qx, p.x), vy = __fsub_rn(qy, p.y), vz = __fsub_rn(qz, p.z);  // :134
+    const float rho = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz)));
+    const float D = __fadd_rn(w1, rho);
+    const float mx = __fdiv_rn(__fadd_rn(__fmul_rn(nv.x, w1), __fmul_rn(vx, rho)), D);  // :136
+    const float my = __fdiv_rn(__fadd_rn(__fmul_rn(nv.y, w1), __fmul_rn(vy, rho)), D);
+    const float mz = __fdiv_rn(__fadd_rn(__fmul_rn(nv.z, w1), __fmul_rn(vz, rho)), D);
+    const float dot = __fadd_rn(__fadd_rn(__fmul_rn(vx, mx), __fmul_rn(vy, my)), __fmul_rn(vz, mz));
+    ds = __fadd_rn(ds, __fmul_rn(w[k], dot));  // :137-142
+    // d(dot)/dx = (w1 n + 3 rho v) / D - dot * v / (rho D)   (norm's sub-gradient at rho = 0 is 0)
+    const float invD = 1.0f / D;
+    const float c2 = rho > 0.f ? dot / (rho * D) : 0.f;
+    grad[0] += w[k] * ((w1 * nv.x + 3.f * rho * vx) * invD - c2 * vx);
+    grad[1] += w[k] * ((w1 * nv.y + 3.f * rho * vy) * invD - c2 * vy);
+    grad[2] += w[k] * ((w1 * nv.z + 3.f * rho * vz) * invD - c2 * vz);
+  }
+}
+
+__global__ void __launch_bounds__(128)
+knn_distance_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts,
+                    const float4* __restrict__ indicator, float w1, PointSrc src, int64_t P, KnnOut out) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float qx, qy, qz;
+  load_query(src, p, qx, qy, qz);
+  float d2[KNN_K];
+  int32_t ix[KNN_K];
+  knn_walk<KNN_K>(nodes, pts, qx, qy, qz, d2, ix);
+  float w[KNN_K], ds, grad[3];
+  mesh_distance_point(pts, indicator, w1, qx, qy, qz, d2, ix, w, ds, grad);
+  out.ds[p] = ds;
+#pragma unroll
+  for (int k = 0; k < KNN_K; ++k) {
+    out.slot[k * out.stride + p] = ix[k];
+    out.w[k * out.stride + p] = w[k];
+  }
+  if (out.grad) {
+    out.grad[0 * out.stride + p] = grad[0];
+    out.grad[1 * out.stride + p] = grad[1];
+    out.grad[2 * out.stride + p] = grad[2];
+  }
+}
+
+int launch_knn_distance(const nmb_grid* g, const float4* indicator_sorted, float w1, PointSrc src, int64_t P,
+                        KnnOut out, cudaStream_t stream) {
+  if (P <= 0) return 0;
+  knn_distance_kernel<<<(unsigned)ceil_div(P, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src,
+                                                                      P, out);
+  NMB_LAUNCH_OK();
+  return 0;
+}
+
+// renderer.py:79-90,94-95 (compute_bounded_near_far): `n_grid` samples along each ray's sphere chord; keep the min /
+// max depth whose mesh distance is below `thresh`.  Nothing per-sample is stored: the two extrema are reduced with
+// integer atomics on the (non-negative) depth bit patterns.
+__global__ void __launch_bounds__(128)
+bound_scan_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts,
+                  const float4* __restrict__ indicator, float w1, const float* __restrict__ rays_o,
+                  const float* __restrict__ dirs, const float* __restrict__ near, const float* __restrict__ far,
+                  int64_t R, int n_grid, float thresh, int32_t* __restrict__ bnear, int32_t* __restrict__ bfar) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= R * n_grid) return;
+  const int64_t r = i % R;
+  const int s = (int)(i / R);
+  const float t = linspace01(s, n_grid);
+  const float d = __fadd_rn(__fmul_rn(near[r], __fsub_rn(1.0f, t)), __fmul_rn(far[r], t));  // renderer.py:81
+  const float qx = __fadd_rn(rays_o[r * 3 + 0], __fmul_rn(d, dirs[r * 3 + 0]));
+  const float qy = __fadd_rn(rays_o[r * 3 + 1], __fmul_rn(d, dirs[r * 3 + 1]));
+  const float qz = __fadd_rn(rays_o[r * 3 + 2], __fmul_rn(d, dirs[r * 3 + 2]));
+  float d2[KNN_K];
+  int32_t ix[KNN_K];
+  knn_walk<KNN_K>(nodes, pts, qx, qy, qz, d2, ix);
+  float w[KNN_K], ds, grad[3];
+  mesh_distance_point(pts, indicator, w1, qx, qy, qz, d2, ix, w, ds, grad);
+  if (ds < thresh) {
+    atomicMin(&bnear[r], __float_as_int(d));
+    atomicMax(&bfar[r], __float_as_int(d));
+  }
+}
+
+int launch_bound_scan(const nmb_grid* g, const float4* indicator, float w1, const float* rays_o, const float* dirs,
+                      const float* near, const float* far, int64_t R, int n_grid, float thresh, int32_t* bnear,
+                      int32_t* bfar, cudaStream_t stream) {
+  const int64_t n = R * n_grid;
+  if (n <= 0) return 0;
+  bound_scan_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator, w1, rays_o, dirs,
+                                                                    near, far, R, n_grid, thresh, bnear, bfar);
+  NMB_LAUNCH_OK();
+  return 0;
+}
+
+// Generic K (<= 32) for the frnn shim: candidates kept in a local-memory list.
+__global__ void __launch_bounds__(128)
+knn_generic_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts, const float* __restrict__ xyz,
+                   int64_t M, int K, float r2, float* __restrict__ d2_out, int64_t* __restrict__ idx_out) {
+  const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float qx = xyz[m * 3], qy = xyz[m * 3 + 1], qz = xyz[m * 3 + 2];
+  float d[32];
+  int32_t ix[32];
+  for (int k = 0; k < K; ++k) {
+    d[k] = CUDART_INF_F;
+    ix[k] = -1;
+  }
+  int32_t sn[STACK_MAX];
+  float sd[STACK_MAX];
+  int sp = 1;
+  sn[0] = 0;
+  sd[0] = 0.f;
+  while (sp > 0) {
+    --sp;
+    const int32_t n = sn[sp];
+    if (sd[sp] >= d[K - 1]) continue;
+    const float4 a = __ldg(&nodes[2 * n]);
+    const float4 b = __ldg(&nodes[2 * n + 1]);
+    const int32_t link = __float_as_int(a.w);
+    const int32_t cnt = __float_as_int(b.w);
+    if (cnt < 0) {
+      for (int32_t i = link; i < link - cnt; ++i) {
+        const float4 p = __ldg(&pts[i]);
+        const float dd = sq_dist_rn(qx, qy, qz, p.x, p.y, p.z);
+        if (dd < d[K - 1]) {
+          int k = K - 1;
+          while (k > 0 && dd < d[k - 1]) {
+            d[k] = d[k - 1];
+            ix[k] = ix[k - 1];
+            --k;
+          }
+          d[k] = dd;
+          ix[k] = __float_as_int(p.w);  // original index
+        }
+      }
+    } else {
+      // push children farthest-first (selection by repeated max over <= 8 entries)
+      float cd[8];
+      for (int c = 0; c < 8; ++c) {
+        cd[c] = -1.f;
+        if (c < cnt) {
+          const float bd = box_dist_rn(qx, qy, qz, __ldg(&nodes[2 * (link + c)]), __ldg(&nodes[2 * (link + c) + 1]));
+          if (bd < d[K - 1]) cd[c] = bd;
+        }
+      }
+      for (int it = 0; it < cnt; ++it) {
+        int best = -1;
+        float bv = -1.f;
+        for (int c = 0; c < cnt; ++c)
+          if (cd[c] > bv) {
+            bv = cd[c];
+            best = c;
+          }
+        if (best < 0) break;
+        if (sp < STACK_MAX) {
+          sn[sp] = link + best;
+          sd[sp] = bv;
+          ++sp;
+        }
+        cd[best] = -1.f;
+      }
+    }
+  }
+  for (int k = 0; k < K; ++k) {
+    const bool ok = (ix[k] >= 0) && (d[k] <= r2);
+    d2_out[m * K + k] = ok ? d[k] : -1.f;
+    idx_out[m * K + k] = ok ? (int64_t)ix[k] : (int64_t)-1;
+  }
+}
+
+// SoA (sorted slots) -> row-major API outputs (original vertex order)
+__global__ void export_knn_kernel(const int32_t* __restrict__ order, KnnOut in, int64_t M, float* __restrict__ ds,
+                                  int64_t* __restrict__ idx, float* __restrict__ w, float* __restrict__ grad) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= M * KNN_K) return;
+  const int64_t m = t / KNN_K;
+  const int k = (int)(t % KNN_K);
+  if (idx) idx[t] = (int64_t)order[in.slot[k * in.stride + m]];
+  if (w) w[t] = in.w[k * in.stride + m];
+  if (k == 0 && ds) ds[m] = in.ds[m];
+  if (k < 3 && grad) grad[m * 3 + k] = in.grad[k * in.stride + m];
+}
+
+__global__ void permute_rows4_kernel(const float* __restrict__ src /*[V,3]*/, const int32_t* __restrict__ order,
+                                     int64_t V, float4* __restrict__ dst) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  const int64_t o = order[i];
+  dst[i] = make_float4(src[o * 3], src[o * 3 + 1], src[o * 3 + 2], 0.f);
+}
+
+int permute_indicator(const nmb_grid* g, const float* indicator, float4* dst, cudaStream_t stream) {
+  permute_rows4_kernel<<<(unsigned)ceil_div(g->V, 256), 256, 0, stream>>>(indicator, g->order.p, g->V, dst);
+  NMB_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace nmb
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int nmb_grid_create(const float* vertices, int64_t V, void* stream, nmb_grid** out) {
+  if (!out) return 2;
+  *out = nullptr;
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
+    nmb::set_error("no CUDA device: neumesh_b200 has no CPU path");
+    return 3;
+  }
+  nmb_grid* g = new nmb_grid();
+  int rc = nmb::build_grid(vertices, V, static_cast<cudaStream_t>(stream), g);
+  if (rc != 0) {
+    delete g;
+    return rc;
+  }
+  *out = g;
+  return 0;
+}
+
+void nmb_grid_destroy(nmb_grid* g) { delete g; }
+
+int64_t nmb_grid_num_vertices(const nmb_grid* g) { return g ? g->V : 0; }
+
+const int32_t* nmb_grid_order(const nmb_grid* g) { return g ? g->order.p : nullptr; }
+
+int nmb_knn(const nmb_grid* g, const float* xyz, int64_t M, int K, float r, float* d2, int64_t* idx, void* stream) {
+  NMB_CHECK(g != nullptr, "null grid");
+  NMB_CHECK(K >= 1 && K <= 32, "K must be in [1,32]");
+  NMB_CHECK(K <= g->V, "K exceeds the number of vertices");
+  if (M <= 0) return 0;
+  nmb::knn_generic_kernel<<<(unsigned)nmb::ceil_div(M, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      g->nodes.p, g->pts.p, xyz, M, K, r * r, d2, idx);
+  NMB_LAUNCH_OK();
+  return 0;
+}
+
+int nmb_mesh_distance(const nmb_grid* g, const float* indicator, float indicator_weight, const float* xyz, int64_t M,
+                      float* ds, int64_t* idx, float* w, float* grad_ds, void* stream_) {
+  NMB_CHECK(g != nullptr, "null grid");
+  if (M <= 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  // scratch: permuted indicator + SoA outputs (API convenience path; the renderer uses packed fields instead)
+  float4* ind = nullptr;
+  float* soa = nullptr;
+  NMB_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&ind), sizeof(float4) * g->V, stream));
+  NMB_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&soa), sizeof(float) * M * 20, stream));
+  int rc = nmb::permute_indicator(g, indicator, ind, stream);
+  if (rc) return rc;
+  nmb::KnnOut out;
+  out.ds = soa;
+  out.slot = reinterpret_cast<int32_t*>(soa + M);
+  out.w = soa + 9 * M;
+  out.grad = soa + 17 * M;
+  out.stride = M;
+  nmb::PointSrc src{xyz, nullptr, nullptr, nullptr, 0};
+  rc = nmb::launch_knn_distance(g, ind, indicator_weight, src, M, out, stream);
+  if (rc) return rc;
+  nmb::export_knn_kernel<<<(unsigned)nmb::ceil_div(M * nmb::KNN_K, 256), 256, 0, stream>>>(g->order.p, out, M, ds, idx,
+                                                                                        w, grad_ds);
+  NMB_LAUNCH_OK();
+  NMB_CUDA_OK(cudaFreeAsync(ind, stream));
+  NMB_CUDA_OK(cudaFreeAsync(soa, stream));
+  return 0;
+}
+
+}  // extern "C"

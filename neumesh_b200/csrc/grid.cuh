@@ -1,0 +1,55 @@
+// Spatial index over mesh vertices: Morton-ordered sparse octree with tight node boxes.
+#pragma once
+#include "common.cuh"
+
+struct nmb_grid {
+  int64_t V = 0;
+  int levels = 0;          // octree depth L (codes have 3*L bits)
+  int num_nodes = 0;
+  float bmin[3] = {0, 0, 0};
+  float inv_cell = 0.f;    // 2^L / cube side
+  nmb::DevBuf<float4> pts;     // [V] sorted by Morton code: x, y, z, __int_as_float(original index)
+  nmb::DevBuf<int32_t> order;  // [V] sorted slot -> original index
+  nmb::DevBuf<int32_t> inv;    // [V] original index -> sorted slot
+  nmb::DevBuf<float4> nodes;   // [2*num_nodes]: {lo.xyz, link}, {hi.xyz, count}; see grid.cu
+};
+
+namespace nmb {
+
+constexpr int KNN_K = 8;          // neighbours used by the field (mesh_grid.py:77 default K=8)
+constexpr int LEAF_MAX = 8;       // nodes with <= LEAF_MAX points are leaves
+constexpr int STACK_MAX = 96;     // traversal stack entries (7 * depth + 8 <= 78 for depth 10)
+
+// Per-point outputs of the fused KNN + mesh-distance kernel, structure-of-arrays with stride `stride`
+// (element (k, p) at [k * stride + p]) so that a warp of consecutive points reads/writes coalesced.
+struct KnnOut {
+  float* ds;        // [P]
+  int32_t* slot;    // [8][P] neighbour slots in SORTED order
+  float* w;         // [8][P]
+  float* grad;      // [3][P] d ds / d xyz (nullable)
+  int64_t stride;
+};
+
+// points given explicitly (xyz [P,3] row-major) or as rays: xyz = o[r] + z[p] * d[r], p = s * R + r
+struct PointSrc {
+  const float* xyz;     // explicit points, or nullptr
+  const float* rays_o;  // [R,3]
+  const float* rays_d;  // [R,3]
+  const float* z;       // [S][R] sample-major depths
+  int64_t R;
+};
+
+// torch.linspace(0, 1, n)[i] in fp32: step * i below the midpoint, fma(-step, n-1-i, 1) above (ATen's CPU kernel)
+__device__ __forceinline__ float linspace01(int i, int n) {
+  const float step = __fdiv_rn(1.0f, (float)(n - 1));
+  return (i < n / 2) ? __fmul_rn(step, (float)i) : fmaf(-step, (float)(n - 1 - i), 1.0f);
+}
+
+int launch_bound_scan(const nmb_grid* g, const float4* indicator, float w1, const float* rays_o, const float* dirs,
+                      const float* near, const float* far, int64_t R, int n_grid, float thresh, int32_t* bnear,
+                      int32_t* bfar, cudaStream_t stream);
+
+int launch_knn_distance(const nmb_grid* g, const float4* indicator_sorted, float w1, PointSrc src, int64_t P,
+                        KnnOut out, cudaStream_t stream);
+
+}  // namespace nmb

@@ -1,0 +1,455 @@
+// volume_render (models/renderer.py:105-368) for a NeuMesh field: per-ray sample placement, field evaluation and
+// alpha compositing, un-batched, perturb = False, no grad.
+//
+// Data layout: every per-sample array of a ray chunk is SAMPLE-MAJOR, element (sample s, ray r) at [s * R + r].
+// A warp therefore holds 32 neighbouring rays at one sample index: the per-ray kernels (one thread per ray) read
+// and write fully coalesced, and the per-point kernels (KNN walk, MLP tiles) see spatially coherent points.
+//
+// Per chunk:  rays -> sphere near/far -> [256-sample mesh-distance scan -> bounded near/far]
+//             -> 64 coarse samples -> 4 x { slope/alpha/cdf -> 16 inverse-cdf samples -> sdf -> merge }
+//             -> sdf(+nabla) at the 128 samples, sdf+nabla+colour at the 127 mid-points -> composite.
+#include <math_constants.h>
+
+#include "field.cuh"
+
+namespace nmb {
+
+constexpr int RT = 128;  // threads per block of the per-ray kernels
+
+__device__ __forceinline__ float sigmoid_t(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+// renderer.py:150-153 (normalise directions) + rend_util.py:179-199 (sphere near/far)
+__global__ void ray_setup_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, int64_t R,
+                                 float radius, int normalize, float* __restrict__ dirs, float* __restrict__ near,
+                                 float* __restrict__ far, int32_t* __restrict__ bnear, int32_t* __restrict__ bfar) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  float dx = rays_d[r * 3], dy = rays_d[r * 3 + 1], dz = rays_d[r * 3 + 2];
+  if (normalize) {
+    // F.normalize: v / max(||v||, 1e-12)
+    const float n = fmaxf(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))), 1e-12f);
+    dx = __fdiv_rn(dx, n);
+    dy = __fdiv_rn(dy, n);
+    dz = __fdiv_rn(dz, n);
+  }
+  dirs[r * 3] = dx;
+  dirs[r * 3 + 1] = dy;
+  dirs[r * 3 + 2] = dz;
+  const float ox = rays_o[r * 3], oy = rays_o[r * 3 + 1], oz = rays_o[r * 3 + 2];
+  const float mid = -__fadd_rn(__fadd_rn(__fmul_rn(ox, dx), __fmul_rn(oy, dy)), __fmul_rn(oz, dz));
+  near[r] = fmaxf(__fsub_rn(mid, radius), 0.f);
+  far[r] = fmaxf(__fadd_rn(mid, radius), radius);
+  bnear[r] = 0x7f800000;  // +inf as ordered int (depths are >= 0)
+  bfar[r] = -1;
+}
+
+// renderer.py:91-101
+__global__ void bound_finish_kernel(int64_t R, const int32_t* __restrict__ bnear, const int32_t* __restrict__ bfar,
+                                    float* __restrict__ near, float* __restrict__ far) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  float n = near[r], f = far[r];
+  if (bfar[r] >= 0) {  // at least one sample inside the shell: both extrema exist
+    n = __int_as_float(bnear[r]);
+    f = __int_as_float(bfar[r]);
+  }
+  if (__fsub_rn(f, n) < 0.1f) {
+    f = __fadd_rn(f, 0.05f);
+    n = __fsub_rn(n, 0.05f);
+  }
+  near[r] = n;
+  far[r] = f;
+}
+
+__global__ void bypass_kernel(int64_t R, int use_near, float nb, int use_far, float fb, float* __restrict__ near,
+                              float* __restrict__ far) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  if (use_near) near[r] = nb;
+  if (use_far) far[r] = fb;
+}
+
+// renderer.py:193-194: z[s][r] = near * (1 - t_s) + far * t_s
+__global__ void coarse_z_kernel(int64_t R, int S, const float* __restrict__ near, const float* __restrict__ far,
+                                float* __restrict__ z) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= R * S) return;
+  const int64_t r = i % R;
+  const int s = (int)(i / R);
+  const float t = linspace01(s, S);
+  z[i] = __fadd_rn(__fmul_rn(near[r], __fsub_rn(1.0f, t)), __fmul_rn(far[r], t));
+}
+
+// One up-sampling iteration for one ray (renderer.py:209-245 + rend_util.py:276-319 with det=True).
+// n = current number of samples; writes n_new new depths (ascending) to znew[i][r].
+__global__ void __launch_bounds__(RT)
+upsample_kernel(int64_t R, int n, int n_new, float inv_s, const float* __restrict__ z, const float* __restrict__ sdf,
+                float* __restrict__ wbuf, float* __restrict__ znew) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  // pass 1: weights (sequential cumprod, as torch's CPU cumprod) and their sum
+  float z0 = z[r], s0 = sdf[r];
+  float prev_raw = 0.f;  // "prev_dot_val": raw slope of the previous interval, 0 for the first
+  float T = 1.0f;
+  float total = 0.f;
+  for (int j = 0; j + 1 < n; ++j) {
+    const float z1 = z[(int64_t)(j + 1) * R + r], s1 = sdf[(int64_t)(j + 1) * R + r];
+    const float mid = __fmul_rn(__fadd_rn(s0, s1), 0.5f);
+    const float raw = __fdiv_rn(__fsub_rn(s1, s0), __fadd_rn(__fsub_rn(z1, z0), 1e-5f));
+    float slope = fminf(prev_raw, raw);
+    slope = fminf(fmaxf(slope, -10.0f), 0.0f);
+    prev_raw = raw;
+    const float dist = __fsub_rn(z1, z0);
+    const float half = __fmul_rn(__fmul_rn(slope, dist), 0.5f);
+    const float c0 = sigmoid_t(__fmul_rn(__fsub_rn(mid, half), inv_s));
+    const float c1 = sigmoid_t(__fmul_rn(__fadd_rn(mid, half), inv_s));
+    const float alpha = __fdiv_rn(__fadd_rn(__fsub_rn(c0, c1), 1e-5f), __fadd_rn(c0, 1e-5f));
+    const float w = __fadd_rn(__fmul_rn(alpha, T), 1e-5f);  // alpha_to_w, then sample_pdf's "+ 1e-5"
+    T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f));
+    wbuf[(int64_t)j * R + r] = w;
+    total = __fadd_rn(total, w);
+    z0 = z1;
+    s0 = s1;
+  }
+  // pass 2: inverse CDF at u_i = linspace(0,1,n_new); searchsorted(right=False): first j with cdf[j] >= u
+  int i = 0;
+  float u = linspace01(0, n_new);
+  float cdf_prev = 0.f;           // cdf[j-1]
+  float bin_prev = z[r];          // bins[j-1]
+  float cdf_j = 0.f;              // cdf[0] = 0
+  float bin_j = bin_prev;
+  for (int j = 0; j < n && i < n_new; ++j) {
+    if (j > 0) {
+      cdf_prev = cdf_j;
+      bin_prev = bin_j;
+      cdf_j = __fadd_rn(cdf_j, __fdiv_rn(wbuf[(int64_t)(j - 1) * R + r], total));
+      bin_j = z[(int64_t)j * R + r];
+    }
+    while (i < n_new && cdf_j >= u) {
+      // inds = j: below = max(j-1, 0), above = min(j, n-1) = j
+      const float cb = (j > 0) ? cdf_prev : cdf_j;
+      const float bb = (j > 0) ? bin_prev : bin_j;
+      float denom = __fsub_rn(cdf_j, cb);
+      if (denom < 1e-5f) denom = 1.0f;
+      const float t = __fdiv_rn(__fsub_rn(u, cb), denom);
+      znew[(int64_t)i * R + r] = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(bin_j, bb)));
+      ++i;
+      if (i < n_new) u = linspace01(i, n_new);
+    }
+  }
+  // u above the last cdf entry: inds = n -> below = above = n-1 -> denom = 0 -> 1 -> sample = bins[n-1]
+  for (; i < n_new; ++i) znew[(int64_t)i * R + r] = bin_j;
+}
+
+// Merge the n_new ascending new samples into the n sorted ones (renderer.py:246,256-258: cat + sort + gather),
+// in place, from the back.  Ties: either order is equivalent (tied depths carry bit-identical sdf values).
+__global__ void __launch_bounds__(RT)
+merge_kernel(int64_t R, int n, int n_new, float* __restrict__ z, float* __restrict__ sdf,
+             const float* __restrict__ znew, const float* __restrict__ sdfnew) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  int a = n - 1, b = n_new - 1;
+  float za = z[(int64_t)a * R + r], zb = znew[(int64_t)b * R + r];
+  for (int o = n + n_new - 1; o >= 0 && b >= 0; --o) {
+    if (a >= 0 && za > zb) {
+      z[(int64_t)o * R + r] = za;
+      sdf[(int64_t)o * R + r] = sdf[(int64_t)a * R + r];
+      --a;
+      if (a >= 0) za = z[(int64_t)a * R + r];
+    } else {
+      z[(int64_t)o * R + r] = zb;
+      sdf[(int64_t)o * R + r] = sdfnew[(int64_t)b * R + r];
+      --b;
+      if (b >= 0) zb = znew[(int64_t)b * R + r];
+    }
+  }
+}
+
+// renderer.py:266: d_mid = 0.5 * (d_all[1:] + d_all[:-1])
+__global__ void midpoints_kernel(int64_t R, int P, const float* __restrict__ z, float* __restrict__ zmid) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= R * (P - 1)) return;
+  zmid[i] = __fmul_rn(0.5f, __fadd_rn(z[i + R], z[i]));
+}
+
+// renderer.py:17-24 (sdf_to_alpha), :49-63 (alpha_to_w), :299-333 (integration, white background, normals)
+__global__ void __launch_bounds__(RT)
+composite_kernel(int64_t R, int P, float s, int white_bkgd, const float* __restrict__ sdf, const float* __restrict__ zmid,
+                 const float* __restrict__ rgb_s /*[3][(P-1)*R]*/, int64_t cstride,
+                 const float* __restrict__ nabla_s /*[3][P*R] or null*/, int64_t nstride, float* __restrict__ wbuf,
+                 float* __restrict__ rgb_out, float* __restrict__ depth_out, float* __restrict__ acc_out,
+                 float* __restrict__ normals_out) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  float c0 = sigmoid_t(__fmul_rn(sdf[r], s));
+  float T = 1.0f, acc = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+  for (int j = 0; j + 1 < P; ++j) {
+    const int64_t q = (int64_t)j * R + r;
+    const float c1 = sigmoid_t(__fmul_rn(sdf[q + R], s));
+    const float alpha = fmaxf(__fdiv_rn(__fsub_rn(c0, c1), __fadd_rn(c0, 1e-10f)), 0.f);
+    const float w = __fmul_rn(alpha, T);
+    T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f));
+    wbuf[q] = w;
+    acc = __fadd_rn(acc, w);
+    cr = __fadd_rn(cr, __fmul_rn(w, rgb_s[q]));
+    cg = __fadd_rn(cg, __fmul_rn(w, rgb_s[cstride + q]));
+    cb = __fadd_rn(cb, __fmul_rn(w, rgb_s[2 * cstride + q]));
+    if (nabla_s) {
+      const float gx = nabla_s[q], gy = nabla_s[nstride + q], gz = nabla_s[2 * nstride + q];
+      const float nn = fmaxf(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz))), 1e-12f);
+      nx = __fadd_rn(nx, __fmul_rn(__fdiv_rn(gx, nn), w));
+      ny = __fadd_rn(ny, __fmul_rn(__fdiv_rn(gy, nn), w));
+      nz = __fadd_rn(nz, __fmul_rn(__fdiv_rn(gz, nn), w));
+    }
+    c0 = c1;
+  }
+  const float den = __fadd_rn(acc, 1e-10f);
+  float depth = 0.f;
+  for (int j = 0; j + 1 < P; ++j) {
+    const int64_t q = (int64_t)j * R + r;
+    depth = __fadd_rn(depth, __fmul_rn(__fdiv_rn(wbuf[q], den), zmid[q]));
+  }
+  if (white_bkgd) {
+    const float bg = __fsub_rn(1.0f, acc);
+    cr = __fadd_rn(cr, bg);
+    cg = __fadd_rn(cg, bg);
+    cb = __fadd_rn(cb, bg);
+  }
+  rgb_out[r * 3] = cr;
+  rgb_out[r * 3 + 1] = cg;
+  rgb_out[r * 3 + 2] = cb;
+  depth_out[r] = depth;
+  acc_out[r] = acc;
+  if (normals_out) {
+    normals_out[r * 3] = nx;
+    normals_out[r * 3 + 1] = ny;
+    normals_out[r * 3 + 2] = nz;
+  }
+}
+
+// [S][R] sample-major -> [R,S] row-major (detail outputs); C channels with source stride cstride: out [R,S,C]
+__global__ void export_samples_kernel(int64_t R, int S, int C, const float* __restrict__ src, int64_t cstride,
+                                      float* __restrict__ dst) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= R * S * C) return;
+  const int c = (int)(i % C);
+  const int64_t t = i / C;
+  const int s = (int)(t % S);
+  const int64_t r = t / S;
+  dst[i] = src[c * cstride + (int64_t)s * R + r];
+}
+
+__global__ void export_near_far_kernel(int64_t R, const float* __restrict__ near, const float* __restrict__ far,
+                                       float* __restrict__ dst) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  dst[r * 2] = near[r];
+  dst[r * 2 + 1] = far[r];
+}
+
+// utils/rend_util.py:97-176: pixel (x, y) -> K^-1 -> normalise -> rotate
+__global__ void get_rays_kernel(int H, int W, float fx, float fy, float cx, float cy, float sk, float r00, float r01,
+                                float r02, float r10, float r11, float r12, float r20, float r21, float r22, float tx,
+                                float ty, float tz, float* __restrict__ rays_o, float* __restrict__ rays_d) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)H * W) return;
+  const float x = (float)(i % W), y = (float)(i / W);
+  // lift(): x_lift = (x - cx + cy*sk/fy - sk*y/fy) / fx * z ; y_lift = (y - cy) / fy * z ; z = 1
+  const float xl = __fdiv_rn(__fsub_rn(__fadd_rn(__fsub_rn(x, cx), __fdiv_rn(__fmul_rn(cy, sk), fy)),
+                                        __fdiv_rn(__fmul_rn(sk, y), fy)), fx);
+  const float yl = __fdiv_rn(__fsub_rn(y, cy), fy);
+  const float n = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(xl, xl), __fmul_rn(yl, yl)), 1.0f));
+  const float dx = __fdiv_rn(xl, n), dy = __fdiv_rn(yl, n), dz = __fdiv_rn(1.0f, n);
+  rays_d[i * 3 + 0] = r00 * dx + r01 * dy + r02 * dz;
+  rays_d[i * 3 + 1] = r10 * dx + r11 * dy + r12 * dz;
+  rays_d[i * 3 + 2] = r20 * dx + r21 * dy + r22 * dz;
+  rays_o[i * 3 + 0] = tx;
+  rays_o[i * 3 + 1] = ty;
+  rays_o[i * 3 + 2] = tz;
+}
+
+}  // namespace nmb
+
+namespace {
+
+struct Workspace {
+  // all sizes in floats
+  float *dirs, *near, *far;
+  int32_t *bnear, *bfar;
+  float *z, *sdf, *znew, *sdfnew, *wbuf, *zmid;
+  float *k_ds, *k_w, *k_grad;
+  int32_t* k_slot;
+  float *nabla_pts, *nabla_mid, *sdf_mid, *rgb;
+  int64_t total;
+};
+
+Workspace carve(void* base, int64_t R, int P, int n_new) {
+  Workspace w{};
+  float* p = static_cast<float*>(base);
+  int64_t off = 0;
+  auto take = [&](int64_t n) {
+    float* q = p ? p + off : nullptr;
+    off += nmb::align_up(n, 64);
+    return q;
+  };
+  const int64_t PR = (int64_t)P * R;
+  w.dirs = take(3 * R);
+  w.near = take(R);
+  w.far = take(R);
+  w.bnear = reinterpret_cast<int32_t*>(take(R));
+  w.bfar = reinterpret_cast<int32_t*>(take(R));
+  w.z = take(PR);
+  w.sdf = take(PR);
+  w.znew = take((int64_t)n_new * R);
+  w.sdfnew = take((int64_t)n_new * R);
+  w.wbuf = take(PR);
+  w.zmid = take(PR);
+  w.k_ds = take(PR);
+  w.k_slot = reinterpret_cast<int32_t*>(take(8 * PR));
+  w.k_w = take(8 * PR);
+  w.k_grad = take(3 * PR);
+  w.nabla_pts = take(3 * PR);
+  w.nabla_mid = take(3 * PR);
+  w.sdf_mid = take(PR);
+  w.rgb = take(3 * PR);
+  w.total = off;
+  return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t nmb_render_workspace_bytes(const nmb_render_cfg* cfg, int64_t rays_per_chunk) {
+  if (!cfg || rays_per_chunk <= 0) return 0;
+  const int P = cfg->N_samples + cfg->N_importance;
+  const int n_new = cfg->N_upsample_iters > 0 ? cfg->N_importance / cfg->N_upsample_iters : 0;
+  return carve(nullptr, rays_per_chunk, P, n_new > 0 ? n_new : 1).total * (int64_t)sizeof(float) + 256;
+}
+
+int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_o, const float* rays_d, int64_t N,
+               int64_t rays_per_chunk, float* rgb, float* depth, float* acc, float* normals,
+               const nmb_render_detail* detail, void* workspace, int64_t workspace_bytes, void* stream_) {
+  using namespace nmb;
+  NMB_CHECK(f && cfg && rays_o && rays_d && rgb && depth && acc, "null argument");
+  NMB_CHECK(rays_per_chunk > 0, "rays_per_chunk must be positive");
+  NMB_CHECK(cfg->N_samples >= 2, "N_samples must be >= 2");
+  NMB_CHECK(cfg->N_upsample_iters >= 0 && (cfg->N_upsample_iters == 0 || cfg->N_importance % cfg->N_upsample_iters == 0),
+            "N_importance must be a multiple of N_upsample_iters");
+  NMB_CHECK(!cfg->calc_normal || normals, "calc_normal needs a normals output");
+  NMB_CHECK(workspace_bytes >= nmb_render_workspace_bytes(cfg, rays_per_chunk), "workspace too small");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int n_iters = cfg->N_upsample_iters;
+  const int n_new = n_iters > 0 ? cfg->N_importance / n_iters : 0;
+  const int P = cfg->N_samples + n_new * n_iters;
+  void* ws_aligned = reinterpret_cast<void*>(align_up(reinterpret_cast<int64_t>(workspace), 256));
+  const nmb_grid* g = f->grid;
+
+  for (int64_t c0 = 0; c0 < N; c0 += rays_per_chunk) {
+    const int64_t R = (N - c0 < rays_per_chunk) ? (N - c0) : rays_per_chunk;
+    Workspace w = carve(ws_aligned, R, P, n_new > 0 ? n_new : 1);
+    const float* ro = rays_o + c0 * 3;
+    const unsigned rb = (unsigned)ceil_div(R, RT);
+    ray_setup_kernel<<<rb, RT, 0, stream>>>(ro, rays_d + c0 * 3, R, cfg->obj_bounding_radius, cfg->normalize_dirs,
+                                            w.dirs, w.near, w.far, w.bnear, w.bfar);
+    NMB_LAUNCH_OK();
+    if (cfg->bounded_near_far) {
+      int rc = launch_bound_scan(g, f->indicator.p, f->w1, ro, w.dirs, w.near, w.far, R, 256, 0.1f, w.bnear, w.bfar,
+                                 stream);
+      if (rc) return rc;
+      bound_finish_kernel<<<rb, RT, 0, stream>>>(R, w.bnear, w.bfar, w.near, w.far);
+      NMB_LAUNCH_OK();
+    }
+    if (cfg->use_near_bypass || cfg->use_far_bypass) {
+      bypass_kernel<<<rb, RT, 0, stream>>>(R, cfg->use_near_bypass, cfg->near_bypass, cfg->use_far_bypass,
+                                           cfg->far_bypass, w.near, w.far);
+      NMB_LAUNCH_OK();
+    }
+    int n = cfg->N_samples;
+    coarse_z_kernel<<<(unsigned)ceil_div(R * n, 256), 256, 0, stream>>>(R, n, w.near, w.far, w.z);
+    NMB_LAUNCH_OK();
+
+    auto eval = [&](const float* zarr, int S, float* sdf_out, float* nabla_out, bool color) -> int {
+      const int64_t Pn = (int64_t)S * R;
+      KnnOut ko{w.k_ds, w.k_slot, w.k_w, w.k_grad, (int64_t)P * R};
+      PointSrc src{nullptr, ro, w.dirs, zarr, R};
+      int rc = launch_knn_distance(g, f->indicator.p, f->w1, src, Pn, ko, stream);
+      if (rc) return rc;
+      FieldIn in{};
+      in.ds = ko.ds;
+      in.slot = ko.slot;
+      in.w = ko.w;
+      in.grad = ko.grad;
+      in.stride = ko.stride;
+      rc = launch_geo(f, in, Pn, sdf_out, nabla_out, stream);
+      if (rc) return rc;
+      if (color) {
+        in.nabla = nabla_out;
+        in.dirs = nullptr;
+        in.rays_d = w.dirs;
+        in.R = R;
+        rc = launch_color(f, in, Pn, w.rgb, stream);
+        if (rc) return rc;
+      }
+      return 0;
+    };
+
+    int rc = eval(w.z, n, w.sdf, nullptr, false);
+    if (rc) return rc;
+    for (int it = 0; it < n_iters; ++it) {
+      upsample_kernel<<<rb, RT, 0, stream>>>(R, n, n_new, 256.0f * (float)(1 << it), w.z, w.sdf, w.wbuf, w.znew);
+      NMB_LAUNCH_OK();
+      rc = eval(w.znew, n_new, w.sdfnew, nullptr, false);
+      if (rc) return rc;
+      merge_kernel<<<rb, RT, 0, stream>>>(R, n, n_new, w.z, w.sdf, w.znew, w.sdfnew);
+      NMB_LAUNCH_OK();
+      n += n_new;
+    }
+    // final samples: sdf at the P points is already known (same points, same kernel => same bits);
+    // calc_normal re-evaluates them with tangents (renderer.py:271-274)
+    if (cfg->calc_normal) {
+      rc = eval(w.z, P, w.sdf, w.nabla_pts, false);
+      if (rc) return rc;
+    }
+    midpoints_kernel<<<(unsigned)ceil_div(R * (P - 1), 256), 256, 0, stream>>>(R, P, w.z, w.zmid);
+    NMB_LAUNCH_OK();
+    const bool need_mid_nabla = f->lay.use_nabla != 0;
+    rc = eval(w.zmid, P - 1, w.sdf_mid, need_mid_nabla ? w.nabla_mid : nullptr, true);
+    if (rc) return rc;
+    composite_kernel<<<rb, RT, 0, stream>>>(R, P, f->s, cfg->white_bkgd, w.sdf, w.zmid, w.rgb, (int64_t)P * R,
+                                            cfg->calc_normal ? w.nabla_pts : nullptr, (int64_t)P * R, w.wbuf,
+                                            rgb + c0 * 3, depth + c0, acc + c0, normals ? normals + c0 * 3 : nullptr);
+    NMB_LAUNCH_OK();
+    if (detail) {
+      auto ex = [&](float* dst, const float* src, int S, int C, int64_t cstride) -> int {
+        if (!dst) return 0;
+        export_samples_kernel<<<(unsigned)ceil_div(R * S * C, 256), 256, 0, stream>>>(R, S, C, src, cstride,
+                                                                                    dst + c0 * S * C);
+        NMB_LAUNCH_OK();
+        return 0;
+      };
+      if ((rc = ex(detail->d_all, w.z, P, 1, 0))) return rc;
+      if ((rc = ex(detail->implicit_surface, w.sdf, P, 1, 0))) return rc;
+      if (cfg->calc_normal && (rc = ex(detail->implicit_nablas, w.nabla_pts, P, 3, (int64_t)P * R))) return rc;
+      if ((rc = ex(detail->radiance, w.rgb, P - 1, 3, (int64_t)P * R))) return rc;
+      if ((rc = ex(detail->sdf_mid, w.sdf_mid, P - 1, 1, 0))) return rc;
+      if (detail->near_far) {
+        export_near_far_kernel<<<rb, RT, 0, stream>>>(R, w.near, w.far, detail->near_far + c0 * 2);
+        NMB_LAUNCH_OK();
+      }
+    }
+  }
+  return 0;
+}
+
+int nmb_get_rays(const float* c2w, const float* intr, int32_t H, int32_t W, float* rays_o, float* rays_d,
+                 void* stream) {
+  NMB_CHECK(c2w && intr && rays_o && rays_d && H > 0 && W > 0, "bad argument");
+  nmb::get_rays_kernel<<<(unsigned)nmb::ceil_div((int64_t)H * W, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      H, W, intr[0], intr[1], intr[2], intr[3], intr[4], c2w[0], c2w[1], c2w[2], c2w[4], c2w[5], c2w[6], c2w[8],
+      c2w[9], c2w[10], c2w[3], c2w[7], c2w[11], rays_o, rays_d);
+  NMB_LAUNCH_OK();
+  return 0;
+}
+
+}  // extern "C"
