@@ -132,6 +132,12 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
                int64_t rays_per_chunk, float* rgb, float* depth, float* acc, float* normals,
                const nmb_render_detail* detail, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* One hierarchical up-sampling step (renderer.py:209-245 + utils/rend_util.py:276-319 sample_pdf, det=True):
+ * from n sorted depths z and their sdf values, the n_new inverse-CDF depths for sharpness inv_s (= 256 * 2^iter).
+ * SAMPLE-MAJOR arrays: z, sdf [n, N]; z_new [n_new, N]; scratch [n, N]. */
+int nmb_upsample_step(const float* z, const float* sdf, int64_t N, int32_t n, int32_t n_new, float inv_s,
+                      float* z_new, float* scratch, void* stream);
+
 /* Ray generation (utils/rend_util.py:97-176 get_rays/lift, full image, no skew handling beyond K[0,1]).
  * c2w [3,4] or [4,4] row-major (first 3 rows used), intr = {fx, fy, cx, cy, skew}. rays_o, rays_d [H*W,3]. */
 int nmb_get_rays(const float* c2w_host /*HOST 12 floats*/, const float* intr_host /*HOST 5 floats*/, int32_t H,

@@ -1,0 +1,19 @@
+"""neumesh_b200 - B200-native implementation of the NeuMesh volumetric-rendering hot path.
+
+Public surface (mirrors the reference's Python API for this path):
+
+* ``NeuMesh``           <- models/frameworks/neumesh/neumesh.py
+* ``MeshGrid``          <- models/mesh_grid.py
+* ``frnn_grid_points``  <- third-party ``frnn`` (models/mesh_grid.py:64,109)
+* ``volume_render`` / ``SingleRenderer`` <- models/renderer.py
+
+The compute lives in ``lib/libneumesh_b200.so`` (hand-written sm_100a CUDA behind the C ABI of
+``include/neumesh_b200.h``); importing this package does not load it, using it does - and fails loudly if the
+extension is missing: there is no CPU fallback.
+"""
+from .mesh_grid import GridHandle, MeshGrid, MeshPrimitive, frnn_grid_points  # noqa: F401
+from .neumesh import Embedder, NeuMesh, get_embedder, interpolation  # noqa: F401
+from .renderer import SingleRenderer, volume_render  # noqa: F401
+
+__all__ = ["NeuMesh", "MeshGrid", "MeshPrimitive", "GridHandle", "frnn_grid_points", "volume_render",
+           "SingleRenderer", "Embedder", "get_embedder", "interpolation"]

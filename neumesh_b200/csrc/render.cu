@@ -442,6 +442,16 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
   return 0;
 }
 
+int nmb_upsample_step(const float* z, const float* sdf, int64_t N, int32_t n, int32_t n_new, float inv_s, float* z_new,
+                      float* scratch, void* stream) {
+  NMB_CHECK(z && sdf && z_new && scratch && n >= 2 && n_new >= 1, "bad argument");
+  if (N <= 0) return 0;
+  nmb::upsample_kernel<<<(unsigned)nmb::ceil_div(N, nmb::RT), nmb::RT, 0, static_cast<cudaStream_t>(stream)>>>(
+      N, n, n_new, inv_s, z, sdf, scratch, z_new);
+  NMB_LAUNCH_OK();
+  return 0;
+}
+
 int nmb_get_rays(const float* c2w, const float* intr, int32_t H, int32_t W, float* rays_o, float* rays_d,
                  void* stream) {
   NMB_CHECK(c2w && intr && rays_o && rays_d && H > 0 && W > 0, "bad argument");

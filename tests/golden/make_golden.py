@@ -1,0 +1,85 @@
+"""Generate ``tests/golden/*.npz`` by running the UNMODIFIED reference (``/root/reference``) on CPU.
+
+Run in the build container only:  ``python tests/golden/make_golden.py``.
+The reference holds no golden vectors of its own; these files are outputs of the reference's
+Python for the hot path (``models/renderer.py``, ``models/frameworks/neumesh/neumesh.py``, ``models/mesh_grid.py``) with
+the one absent native dependency (``frnn``) replaced by the exact-KNN restatement in ``oracle/knn.py``.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+warnings.filterwarnings("ignore")
+
+import ref_harness  # noqa: E402
+from neumesh_b200 import synth  # noqa: E402
+
+
+def state_digest(sd) -> str:
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().numpy().tobytes())
+    return h.hexdigest()
+
+
+def make_case(name, level, H, W, cfg, render_kwargs, seed):
+    ns = ref_harness.load()
+    mesh = synth.icosphere_mesh(level, seed=seed)
+    sd = synth.make_state_dict(mesh, cfg, seed=seed + 1)
+    model = ref_harness.build_reference_model(mesh, cfg, sd)
+    o, d = synth.frame_rays(H, W, view=3)
+    torch.manual_seed(seed)
+    # point queries: near-surface, mid-range and far-from-mesh points
+    dirs = torch.nn.functional.normalize(torch.randn(600, 3), dim=-1)
+    radii = torch.cat([0.5 + 0.05 * torch.randn(300), 0.2 + 0.8 * torch.rand(200), 1.0 + torch.rand(100)])
+    xyz = dirs * radii[:, None]
+    view = torch.nn.functional.normalize(torch.randn(600, 3), dim=-1)
+    with torch.no_grad():
+        ds, idx, w = model.compute_distance(xyz)
+        sdf0 = model.forward_density_only(xyz)
+    sdf1, nabla = model.forward_with_nablas(xyz.clone())
+    sdf2, rgb = model.forward(xyz.clone(), view)
+    with torch.no_grad():
+        r_rgb, r_depth, ex = ns.renderer.volume_render(o, d, model, detailed_output=True, rayschunk=4096,
+                                                       **render_kwargs)
+    out = dict(
+        level=np.int64(level), H=np.int64(H), W=np.int64(W), seed=np.int64(seed), view=np.int64(3),
+        state_digest=np.array(state_digest(sd)),
+        xyz=xyz.numpy(), view_dirs=view.numpy(), ds=ds.numpy(), idx=idx.numpy(), w=w.numpy(),
+        sdf=sdf0.numpy(), nabla=nabla.detach().numpy(), sdf_with_nabla=sdf1.detach().numpy(),
+        rgb_pts=rgb.detach().numpy(), sdf_forward=sdf2.detach().numpy(),
+        rays_o=o.numpy(), rays_d=d.numpy(), render_rgb=r_rgb.numpy(), render_depth=r_depth.numpy(),
+        render_acc=ex["mask_volume"].numpy(), render_d_final=ex["d_final"].numpy(),
+        render_sdf=ex["implicit_surface"].numpy(), render_radiance=ex["radiance"].numpy(),
+    )
+    if "normals_volume" in ex:
+        out["render_normals"] = ex["normals_volume"].numpy()
+    for k, v in render_kwargs.items():
+        out["kw_" + k] = np.array(v)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def main():
+    cfg = synth.ModelConfig()
+    make_case("scan63like_small", 4, 12, 12, cfg,
+              dict(calc_normal=True, white_bkgd=True, bounded_near_far=True), seed=10)
+    cfg2 = synth.ModelConfig(enable_nablas_input=False, ln_s=0.4, learn_indicator_weight=True)
+    make_case("nonabla_unbounded", 3, 10, 10, cfg2,
+              dict(calc_normal=False, white_bkgd=False, bounded_near_far=False), seed=20)
+
+
+if __name__ == "__main__":
+    main()

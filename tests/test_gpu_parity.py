@@ -1,0 +1,430 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ctypes, neumesh_b200/_lib.py), against the CPU
+oracle on identical seeded inputs and against the committed golden vectors of the unmodified reference.
+
+Tolerances (north_star): composited RGB <= 1e-4, composited depth <= 1e-5 max-abs.  Integer / index results
+(neighbour indices) must be bit-exact.  Per-stage tolerances are stated where used.
+
+The reference's sampling cascade is a discrete, rounding-sensitive process (SURVEY.md section 8a': sample_pdf's u=1
+saturation branch, near-flat CDF segments): perturbing the reference's OWN sdf values by one fp32 ulp moves a few
+percent of the rays by more than the tolerance (test_render_noise_floor measures it).  End-to-end parity is therefore
+asserted in two complementary ways:
+  * teacher-forced: the oracle evaluates the field at the CUDA path's own final sample depths and composites -
+    must match on EVERY ray within 1e-4 / 1e-5; each sampling stage is checked with identical inputs
+    (test_upsample_step_*, test_bounded_near_far);
+  * free-running: whole-pipeline agreement, asserted as a fraction of rays not worse than the oracle's own
+    one-ulp noise floor.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from neumesh_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ENGINES = ["fp32", "tcgen05"]
+RGB_TOL, DEPTH_TOL = 1e-4, 1e-5
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device (no CPU fallback exists)")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def case5():
+    cfg = synth.ModelConfig()
+    mesh = synth.icosphere_mesh(5, seed=0)
+    sd = synth.make_state_dict(mesh, cfg, seed=1)
+    return mesh, cfg, sd, helpers.oracle_field(mesh, cfg, sd)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# KNN / mesh distance
+# ---------------------------------------------------------------------------------------------------------------
+def test_knn_exact_vs_brute_force(case5):
+    import neumesh_b200 as nb
+    from oracle import knn as oknn
+    mesh = case5[0]
+    dev = _dev()
+    p = torch.from_numpy(mesh.vertices).float()
+    g = nb.GridHandle(p.to(dev))
+    q, _ = helpers.sample_points(20000, seed=3)
+    q = torch.cat([q, torch.zeros(1, 3), p[:50], 5.0 * torch.ones(1, 3)])  # centre, on-vertex, far outside
+    d_ref, i_ref = oknn.knn_exact(q, p, 8, method="brute")
+    d, i = g.knn(q.to(dev), 8)
+    assert torch.equal(d.cpu(), d_ref), "squared distances must be bit-identical to an fp32 brute force"
+    same = (i.cpu() == i_ref)
+    # ties (exactly equal distances) may be ordered differently
+    tie = torch.zeros_like(same)
+    tie[:, 1:] |= d_ref[:, 1:] == d_ref[:, :-1]
+    tie[:, :-1] |= d_ref[:, 1:] == d_ref[:, :-1]
+    assert (same | tie).all()
+    # K = 32 (the MeshGrid.__init__ self-query, mesh_grid.py:64-74) and the frnn call signature
+    dists, idxs, nn_, grid = nb.frnn_grid_points(p[None, :3000].to(dev), p[None].to(dev), None, None, K=32, r=100.0,
+                                                 grid=None, return_nn=False, return_sorted=True)
+    d32, i32 = oknn.knn_exact(p[:3000], p, 32, method="brute")
+    assert dists.shape == (1, 3000, 32) and idxs.dtype == torch.int64 and nn_ is None
+    assert torch.equal(dists[0].cpu(), d32)
+    assert (idxs[0, :, 0].cpu() == torch.arange(3000)).all()  # every vertex is its own nearest neighbour
+    # grid re-use: same handle comes back
+    _, _, _, grid2 = nb.frnn_grid_points(q[None, :10].to(dev), p[None].to(dev), None, None, K=8, r=100.0, grid=grid)
+    assert grid2 is grid
+    # radius padding (FRNN pads with -1 outside r)
+    dr, ir, _, _ = nb.frnn_grid_points(q[None, :100].to(dev), p[None].to(dev), None, None, K=8, r=0.05, grid=grid)
+    ref_in = d_ref[:100] <= 0.05 * 0.05
+    assert torch.equal((ir[0].cpu() >= 0), ref_in)
+
+
+def test_knn_edge_cases():
+    import neumesh_b200 as nb
+    from oracle import knn as oknn
+    dev = _dev()
+    torch.manual_seed(0)
+    # duplicates, collinear clusters, tiny mesh (V = 8), single query, empty query
+    pts = torch.cat([torch.rand(40, 3), torch.rand(5, 3).repeat(4, 1), torch.linspace(0, 1, 30)[:, None].repeat(1, 3)])
+    g = nb.GridHandle(pts.to(dev))
+    q = torch.rand(500, 3) * 2 - 0.5
+    d, i = g.knn(q.to(dev), 8)
+    d_ref, _ = oknn.knn_exact(q, pts, 8, method="brute")
+    assert torch.equal(d.cpu(), d_ref)
+    assert torch.equal(((q[:, None, :] - pts[i.cpu()]) ** 2).sum(-1).float(), ((q[:, None, :] - pts[i.cpu()]) ** 2).sum(-1))
+    g8 = nb.GridHandle(torch.rand(8, 3).to(dev))
+    d8, i8 = g8.knn(torch.rand(3, 3).to(dev), 8)
+    assert sorted(i8[0].tolist()) == list(range(8))
+    d0, i0 = g.knn(torch.empty(0, 3, device=dev), 8)
+    assert d0.shape == (0, 8) and i0.shape == (0, 8)
+    with pytest.raises(RuntimeError):
+        nb.GridHandle(torch.rand(5, 3).to(dev))  # fewer than K vertices
+
+
+def test_mesh_distance_vs_oracle(case5):
+    import neumesh_b200 as nb
+    from oracle.field import mesh_distance
+    mesh, cfg, sd, f = case5
+    dev = _dev()
+    mg = nb.MeshGrid(mesh, dev)
+    x, _ = helpers.sample_points(8000, seed=11)
+    ind = sd["indicator_vector"]
+    xr = x.clone().requires_grad_(True)
+    ds_r, idx_r, w_r = mesh_distance(xr, f.vertices, ind, 0.1)
+    (g_r,) = torch.autograd.grad(ds_r.sum(), xr)
+    ds, idx, w, grad = mg.grid.mesh_distance(x.to(dev), ind.to(dev), 0.1, want_grad=True)
+    assert torch.equal(idx.cpu(), idx_r)
+    assert (w.cpu() - w_r).abs().max() < 2e-7
+    assert (ds.cpu() - ds_r.detach()).abs().max() < 1e-6
+    assert (grad.cpu() - g_r).abs().max() < 2e-5
+    # the public drop-in returns the reference's shapes / dtypes (mesh_grid.py:88-144)
+    ds2, idx2, w2 = mg.compute_distance(x.to(dev), indicator_vector=ind.to(dev), indicator_weight=0.1)
+    assert ds2.shape == (8000, 1) and idx2.shape == (8000, 8) and idx2.dtype == torch.int64 and w2.shape == (8000, 8)
+    # grad-enabled call: torch-op blend on CUDA neighbours, differentiable w.r.t. xyz and the indicator
+    xg = x.to(dev).requires_grad_(True)
+    indg = ind.to(dev).requires_grad_(True)
+    ds3, _, _ = mg.compute_distance(xg, indicator_vector=indg, indicator_weight=0.1)
+    gx, gi = torch.autograd.grad(ds3.sum(), [xg, indg])
+    assert (gx.cpu() - g_r).abs().max() < 2e-5 and gi.abs().sum() > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# field
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("engine", ENGINES)
+def test_field_vs_oracle(case5, engine):
+    mesh, cfg, sd, f = case5
+    dev = _dev()
+    model = helpers.cuda_model(mesh, cfg, sd, engine)
+    x, v = helpers.sample_points(5000, seed=21)  # not a multiple of any tile size: ragged tail
+    with torch.no_grad():
+        sdf = model.forward_density_only(x.to(dev))
+        sdf_n, nabla = model.forward_with_nablas(x.to(dev))
+        sdf_c, rgb = model.forward(x.to(dev), v.to(dev))
+    s_ref = f.forward_density_only(x)
+    _, n_ref = f.forward_with_nablas(x)
+    _, c_ref = f.forward(x, v)
+    e_sdf = (sdf.cpu() - s_ref).abs().max().item()
+    e_sdf_n = (sdf_n.cpu() - s_ref).abs().max().item()
+    e_nab = (nabla.cpu() - n_ref).abs().max().item()
+    e_rgb = (rgb.cpu() - c_ref).abs().max().item()
+    print(f"[{engine}] max-abs: sdf {e_sdf:.3e}  sdf(jvp kernel) {e_sdf_n:.3e}  nabla {e_nab:.3e} "
+          f"(|nabla| max {n_ref.abs().max():.2f})  rgb {e_rgb:.3e}")
+    assert e_sdf < 2e-6 and e_sdf_n < 2e-6      # |sdf| <= ~1: a few fp32 ulps through three 256-wide layers
+    assert e_nab < 5e-5                          # |nabla| ~ 1-3, forward-mode vs the oracle's autograd
+    assert e_rgb < 5e-6
+    assert torch.equal(sdf, sdf_c)               # same points -> same bits from either entry point
+    assert torch.equal(sdf, sdf_n)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", ["scan63like_small.npz", "nonabla_unbounded.npz"])
+def test_field_vs_reference_golden(golden_dir, name, engine):
+    g, mesh, cfg, sd, kw = helpers.golden_case(os.path.join(golden_dir, name))
+    dev = _dev()
+    model = helpers.cuda_model(mesh, cfg, sd, engine)
+    x, v = torch.from_numpy(g["xyz"]).to(dev), torch.from_numpy(g["view_dirs"]).to(dev)
+    with torch.no_grad():
+        ds, idx, w = model.compute_distance(x)
+        sdf, nabla = model.forward_with_nablas(x)
+        _, rgb = model.forward(x, v)
+    assert torch.equal(idx.cpu(), torch.from_numpy(g["idx"]))
+    assert (ds.cpu() - torch.from_numpy(g["ds"])).abs().max() < 1e-6
+    assert (sdf.cpu() - torch.from_numpy(g["sdf"])).abs().max() < 2e-6
+    assert (nabla.cpu() - torch.from_numpy(g["nabla"])).abs().max() < 5e-5
+    assert (rgb.cpu() - torch.from_numpy(g["rgb_pts"])).abs().max() < 5e-6
+
+
+def test_field_edge_cases(case5):
+    mesh, cfg, sd, f = case5
+    dev = _dev()
+    model = helpers.cuda_model(mesh, cfg, sd, "fp32")
+    with torch.no_grad():
+        assert model.forward_density_only(torch.empty(0, 3, device=dev)).shape == (0, 1)
+        one = model.forward_density_only(torch.tensor([[0.1, 0.2, 0.45]], device=dev))
+        assert one.shape == (1, 1) and torch.isfinite(one).all()
+        # leading dims are preserved ([N_rays, N_pts, 3] as batchify_query passes them)
+        x = torch.rand(7, 5, 3, device=dev) - 0.5
+        s, n = model.forward_with_nablas(x)
+        assert s.shape == (7, 5, 1) and n.shape == (7, 5, 3)
+        # a query exactly on a vertex (rho = 0: norm's zero sub-gradient, 1e-7 guard in the weights)
+        v0 = torch.from_numpy(mesh.vertices[:4]).float().to(dev)
+        s0, n0 = model.forward_with_nablas(v0)
+        assert torch.isfinite(s0).all() and torch.isfinite(n0).all()
+    s_ref, n_ref = f.forward_with_nablas(torch.from_numpy(mesh.vertices[:4]).float())
+    assert (s0.cpu() - s_ref).abs().max() < 2e-6 and (n0.cpu() - n_ref).abs().max() < 1e-4
+
+
+def test_repack_on_parameter_change(case5):
+    mesh, cfg, sd, f = case5
+    dev = _dev()
+    model = helpers.cuda_model(mesh, cfg, sd, "fp32")
+    x = (torch.rand(256, 3, device=dev) - 0.5)
+    with torch.no_grad():
+        a = model.forward_density_only(x)
+        model.geometry_features.mul_(1.5)        # in-place update (what an optimiser step does)
+        b = model.forward_density_only(x)
+        model.indicator_vector = torch.nn.Parameter(model.indicator_vector.detach() * 0.5)  # editors re-assign
+        c = model.forward_density_only(x)
+    assert not torch.equal(a, b) and not torch.equal(b, c)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# sampling stages with identical inputs
+# ---------------------------------------------------------------------------------------------------------------
+def test_upsample_step_vs_oracle():
+    from neumesh_b200.renderer import upsample_step
+    from oracle import render as orender
+    dev = _dev()
+    g = torch.Generator().manual_seed(5)
+    N = 4096
+    for it, n in [(0, 64), (1, 80), (2, 96), (3, 112)]:
+        z = torch.sort(2.0 + torch.rand(N, n, generator=g), dim=-1)[0]
+        if it > 0:
+            z[:, 1] = z[:, 0]  # the duplicate of `near` every iteration re-inserts (SURVEY.md section 8a')
+        surf = 2.3 + 0.4 * torch.rand(N, 1, generator=g)
+        sdf = (surf - z) * (0.5 + torch.rand(N, 1, generator=g)) + 0.002 * torch.randn(N, n, generator=g)
+        sdf[: N // 8] = 0.3 + 0.05 * torch.rand(N // 8, n, generator=g)  # rays that miss: flat pdf
+        s0, s1, z0, z1 = sdf[..., :-1], sdf[..., 1:], z[..., :-1], z[..., 1:]
+        mid = (s0 + s1) * 0.5
+        raw = (s1 - s0) / (z1 - z0 + 1e-5)
+        slope = torch.minimum(torch.cat([torch.zeros_like(raw[..., :1]), raw[..., :-1]], -1), raw).clamp(-10.0, 0.0)
+        inv_s = 256 * 2 ** it
+        c0 = torch.sigmoid((mid - slope * (z1 - z0) * 0.5) * inv_s)
+        c1 = torch.sigmoid((mid + slope * (z1 - z0) * 0.5) * inv_s)
+        w = orender.transmittance_weights((c0 - c1 + 1e-5) / (c0 + 1e-5))
+        ref = orender.inverse_cdf_samples(z, w, 16)
+        out = upsample_step(z.to(dev), sdf.to(dev), 16, float(inv_s)).cpu()
+        err = (out - ref).abs()
+        # interior quantiles must agree tightly; u = 1 (last column) is the saturation branch: it must land on a
+        # bin edge at or after the oracle's up to rounding, and is excluded from the tight comparison
+        tight = err[:, :-1]
+        frac_bad = (tight > 2e-5).float().mean().item()
+        print(f"iter {it}: max err interior {tight.max():.3e}, frac > 2e-5: {frac_bad:.2e}; "
+              f"last-column mismatches {(err[:, -1] > 1e-6).float().mean():.3f}")
+        assert frac_bad < 2e-3  # flat-CDF hits (u inside a ~1e-5-wide plateau) are the only allowed outliers
+        assert (out[:, 1:] >= out[:, :-1]).all() and torch.equal(out[:, 0], z[:, 0])
+
+
+@pytest.mark.parametrize("engine", ["fp32"])
+def test_bounded_near_far_vs_oracle(case5, engine):
+    from neumesh_b200.renderer import render_fused
+    from oracle import render as orender
+    mesh, cfg, sd, f = case5
+    dev = _dev()
+    model = helpers.cuda_model(mesh, cfg, sd, engine)
+    o, d = synth.frame_rays(48, 48, view=2)
+    with torch.no_grad():
+        out = render_fused(o.to(dev), d.to(dev), model, detailed_output=True, N_upsample_iters=0, N_importance=0)
+    dn = torch.nn.functional.normalize(d, dim=-1)
+    near, far = orender.sphere_near_far(o, dn, 1.0)
+    near, far = orender.mesh_bounded_near_far(f, o, dn, near, far)
+    nf = out["near_far"].cpu()
+    bad = ((nf[:, 0:1] - near).abs() > 1e-6) | ((nf[:, 1:2] - far).abs() > 1e-6)
+    print("near/far mismatching rays:", int(bad.sum()), "of", bad.shape[0])
+    assert bad.float().mean() < 0.005  # a ds within one ulp of the 0.1 threshold may flip one grid step
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# end to end
+# ---------------------------------------------------------------------------------------------------------------
+def _teacher_forced(f, o, d, z_all, calc_normal, white_bkgd):
+    """Oracle field + oracle compositing at given sample depths (renderer.py:264-333)."""
+    from oracle import render as orender
+    dn = torch.nn.functional.normalize(d, dim=-1)
+    pts = o[:, None, :] + z_all[..., None] * dn[:, None, :]
+    z_mid = 0.5 * (z_all[..., 1:] + z_all[..., :-1])
+    pm = o[:, None, :] + z_mid[..., None] * dn[:, None, :]
+    if calc_normal:
+        sdf, nab = f.forward_with_nablas(pts)
+    else:
+        sdf, nab = f.forward_density_only(pts), None
+    sdf = sdf.squeeze(-1)
+    cdf = torch.sigmoid(sdf * f.forward_s())
+    alpha = ((cdf[..., :-1] - cdf[..., 1:]) / (cdf[..., :-1] + 1e-10)).clamp_min(0)
+    _, rad = f.forward(pm, dn[:, None, :].expand_as(pm))
+    w = orender.transmittance_weights(alpha)
+    rgb = (w[..., None] * rad).sum(-2)
+    acc = w.sum(-1)
+    depth = (w / (acc[..., None] + 1e-10) * z_mid).sum(-1)
+    if white_bkgd:
+        rgb = rgb + (1 - acc[..., None])
+    normals = None
+    if calc_normal:
+        nn_ = torch.nn.functional.normalize(nab, dim=-1)
+        normals = (nn_[..., :-1, :] * w[..., None]).sum(-2)
+    return rgb, depth, acc, normals
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_render_teacher_forced(case5, engine):
+    import neumesh_b200 as nb
+    mesh, cfg, sd, f = case5
+    dev = _dev()
+    model = helpers.cuda_model(mesh, cfg, sd, engine)
+    o, d = synth.frame_rays(40, 40, view=5)
+    kw = dict(calc_normal=True, white_bkgd=True, bounded_near_far=True)
+    with torch.no_grad():
+        rgb, depth, ex = nb.volume_render(o.to(dev), d.to(dev), model, detailed_output=True, **kw)
+    z_all = ex["d_all"].cpu()
+    assert z_all.shape == (1600, 128) and (z_all[:, 1:] >= z_all[:, :-1]).all()
+    r_rgb, r_depth, r_acc, r_n = _teacher_forced(f, o, d, z_all, True, True)
+    e_rgb = (rgb.cpu() - r_rgb).abs().max().item()
+    e_dep = (depth.cpu() - r_depth).abs().max().item()
+    e_acc = (ex["mask_volume"].cpu() - r_acc).abs().max().item()
+    e_nrm = (ex["normals_volume"].cpu() - r_n).abs().max().item()
+    print(f"[{engine}] teacher-forced max-abs: rgb {e_rgb:.3e} depth {e_dep:.3e} acc {e_acc:.3e} normals {e_nrm:.3e}")
+    assert e_rgb <= RGB_TOL and e_dep <= DEPTH_TOL and e_acc <= 1e-4 and e_nrm <= 5e-4
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_render_free_running_vs_oracle_and_golden(golden_dir, engine):
+    import neumesh_b200 as nb
+    from oracle import render as orender
+    dev = _dev()
+    for name in ["scan63like_small.npz", "nonabla_unbounded.npz"]:
+        g, mesh, cfg, sd, kw = helpers.golden_case(os.path.join(golden_dir, name))
+        model = helpers.cuda_model(mesh, cfg, sd, engine)
+        o, d = torch.from_numpy(g["rays_o"]), torch.from_numpy(g["rays_d"])
+        with torch.no_grad():
+            rgb, depth, ex = nb.volume_render(o.to(dev), d.to(dev), model, detailed_output=False, **kw)
+        dr = (rgb.cpu() - torch.from_numpy(g["render_rgb"])).abs().max(-1)[0]
+        dd = (depth.cpu() - torch.from_numpy(g["render_depth"])).abs()
+        ok = ((dr <= RGB_TOL) & (dd <= DEPTH_TOL)).float().mean().item()
+        print(f"[{engine}] {name}: rays within (1e-4, 1e-5) of the reference's golden render: {ok:.3f}; "
+              f"median rgb {dr.median():.2e} depth {dd.median():.2e}; max rgb {dr.max():.2e} depth {dd.max():.2e}")
+        assert ok >= 0.85 and dr.median() <= 1e-5 and dd.median() <= 2e-6
+        assert set(["rgb", "depth_volume", "mask_volume"]) <= set(ex.keys())
+
+
+def test_render_noise_floor(case5):
+    """How much the ORACLE itself moves when its sdf values are perturbed by ~1 ulp - the yardstick for the
+    free-running comparison (printed; asserts only that the CUDA path is not worse than 3x this floor)."""
+    import neumesh_b200 as nb
+    from oracle import render as orender
+    mesh, cfg, sd, f = case5
+    dev = _dev()
+    o, d = synth.frame_rays(32, 32, view=7)
+    kw = dict(calc_normal=False, white_bkgd=True, bounded_near_far=True)
+    rgb0, dep0, _ = orender.volume_render(o, d, f, **kw)
+
+    class Noisy:
+        def __init__(self, base):
+            self.b, self.g = base, torch.Generator().manual_seed(9)
+
+        def __getattr__(self, k):
+            return getattr(self.b, k)
+
+        def forward_density_only(self, x):
+            y = self.b.forward_density_only(x)
+            return y + 1.2e-7 * torch.randn(y.shape, generator=self.g) * y.abs().clamp_min(0.05)
+
+    rgb1, dep1, _ = orender.volume_render(o, d, Noisy(f), **kw)
+    floor = 1 - (((rgb1 - rgb0).abs().max(-1)[0] <= RGB_TOL) & ((dep1 - dep0).abs() <= DEPTH_TOL)).float().mean().item()
+    res = {}
+    for engine in ENGINES:
+        model = helpers.cuda_model(mesh, cfg, sd, engine)
+        with torch.no_grad():
+            rgb, dep, _ = nb.volume_render(o.to(dev), d.to(dev), model, detailed_output=False, **kw)
+        res[engine] = 1 - (((rgb.cpu() - rgb0).abs().max(-1)[0] <= RGB_TOL)
+                           & ((dep.cpu() - dep0).abs() <= DEPTH_TOL)).float().mean().item()
+    print(f"rays outside (1e-4,1e-5): oracle +-1ulp noise floor {floor:.4f}; CUDA fp32 {res['fp32']:.4f}; "
+          f"CUDA tcgen05 {res['tcgen05']:.4f}")
+    for engine in ENGINES:
+        assert res[engine] <= max(3 * floor, 0.05)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json sizes: V = 163 842, 800 x 800 rays)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("engine", ENGINES)
+def test_full_size_properties(engine):
+    import neumesh_b200 as nb
+    dev = _dev()
+    cfg = synth.ModelConfig()
+    mesh = synth.icosphere_mesh(7, seed=0)
+    sd = synth.make_state_dict(mesh, cfg, seed=1)
+    model = helpers.cuda_model(mesh, cfg, sd, engine)
+    o, d = synth.frame_rays(800, 800, view=0)
+    sel = torch.arange(0, 640000, 5)[:100000]  # 100k rays spread over the frame
+    o, d = o[sel].to(dev), d[sel].to(dev)
+    kw = dict(calc_normal=True, white_bkgd=True, bounded_near_far=True, detailed_output=False)
+    from neumesh_b200.renderer import render_fused
+    with torch.no_grad():
+        a = render_fused(o, d, model, chunk=100000, **kw)
+        b = render_fused(o, d, model, chunk=8192, **kw)      # chunking changes no arithmetic
+        perm = torch.randperm(o.shape[0], device=dev)
+        c = render_fused(o[perm], d[perm], model, chunk=32768, **kw)  # rays are independent
+    for k in ("rgb", "depth_volume", "mask_volume", "normals_volume"):
+        assert torch.isfinite(a[k]).all(), k
+        assert torch.equal(a[k], b[k]), f"{k}: chunked render differs"
+        assert torch.equal(a[k][perm], c[k]), f"{k}: permuted render differs"
+    acc = a["mask_volume"]
+    assert acc.min() >= 0 and acc.max() <= 1 + 1e-4
+    assert (a["rgb"] >= -1e-5).all() and (a["rgb"] <= 1 + 1e-4).all()
+    hit = acc > 0.99
+    assert hit.float().mean() > 0.02
+    # hit rays: depth lies between the unit-sphere entry and exit, normals are ~unit
+    dn = torch.nn.functional.normalize(d, dim=-1)
+    mid = -(o * dn).sum(-1)
+    assert (a["depth_volume"][hit] > mid[hit] - 1.0 - 0.06).all() and (a["depth_volume"][hit] < mid[hit] + 1.06).all()
+    nrm = a["normals_volume"][hit].norm(dim=-1)
+    assert (nrm > 0.8).float().mean() > 0.95
+    # rays that miss the unit sphere entirely composite to the background
+    o_far = o.clone()
+    o_far[:, 1] += 50.0
+    with torch.no_grad():
+        m = render_fused(o_far[:1000], d[:1000], model, **kw)
+    assert torch.isfinite(m["rgb"]).all()
+
+
+def test_get_rays_matches_synth():
+    from neumesh_b200.renderer import get_rays
+    dev = _dev()
+    pose = synth.spiral_poses(8)[3]
+    H, W, f = 30, 40, 55.5
+    K = np.array([[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]], dtype=np.float32)
+    o, d = get_rays(pose, K, H, W, device=dev)
+    o_ref, d_ref = synth.pinhole_rays(pose, H, W, f, f, W / 2, H / 2)
+    assert (o.cpu() - o_ref).abs().max() < 1e-6 and (d.cpu() - d_ref).abs().max() < 1e-6
