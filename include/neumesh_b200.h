@@ -35,6 +35,13 @@ int nmb_version(void);
 /* number of kernels this library has launched in the calling process since load (bench.py: gpu_launches) */
 int64_t nmb_launch_count(void);
 
+/* Per-kernel-class device timing for roofline reports (bench.py): when enabled, CUDA events are recorded on the
+ * launching stream around every launch of a class; collect() synchronises those events and returns, per class
+ * {0 knn+distance, 1 bounded-near/far scan, 2 geometry MLP, 3 geometry MLP + tangents, 4 colour MLP, 5 samplers},
+ * the summed milliseconds, number of launches and number of points processed, then resets the log. */
+void nmb_profile_enable(int on);
+int nmb_profile_collect(double* ms, int64_t* launches, int64_t* units, int n_classes);
+
 /* ---- spatial index ------------------------------------------------------------------------------------------
  * Replaces the cached grid built by MeshGrid.__init__ (models/mesh_grid.py:64-74: a V x V, K=32 FRNN self-query
  * whose only kept result is the `grid` tuple).  Builds a Morton-ordered sparse octree with tight node boxes.

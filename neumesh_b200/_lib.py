@@ -49,6 +49,8 @@ SIGNATURES = {
     "nmb_last_error": (C.c_char_p, []),
     "nmb_version": (C.c_int, []),
     "nmb_launch_count": (_I64, []),
+    "nmb_profile_enable": (None, [C.c_int]),
+    "nmb_profile_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(_I64), C.POINTER(_I64), C.c_int]),
     "nmb_grid_create": (C.c_int, [_P, _I64, _P, C.POINTER(_P)]),
     "nmb_grid_destroy": (None, [_P]),
     "nmb_grid_num_vertices": (_I64, [_P]),
@@ -109,3 +111,20 @@ def require_cuda(t: torch.Tensor, what: str):
 
 def launch_count() -> int:
     return int(lib().nmb_launch_count())
+
+
+PROFILE_CLASSES = ("knn", "bound_scan", "geo", "geo_jvp", "color", "sampler")
+
+
+def profile_enable(on: bool):
+    lib().nmb_profile_enable(1 if on else 0)
+
+
+def profile_collect():
+    """-> {class: {"ms": float, "launches": int, "points": int}} since the last collect (synchronises)."""
+    n = len(PROFILE_CLASSES)
+    ms = (C.c_double * n)()
+    la = (C.c_int64 * n)()
+    un = (C.c_int64 * n)()
+    lib().nmb_profile_collect(ms, la, un, n)
+    return {k: {"ms": ms[i], "launches": int(la[i]), "points": int(un[i])} for i, k in enumerate(PROFILE_CLASSES)}

@@ -1,5 +1,7 @@
 // Library-wide state of the neumesh_b200 C ABI: error string, launch counter, device queries.
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "../../include/neumesh_b200.h"
 #include "common.cuh"
@@ -19,9 +21,68 @@ int sm_count() {
   }
   return cached;
 }
+
+// ---- profiling ----
+struct ProfRec {
+  cudaEvent_t a, b;
+  int tag;
+  int64_t units;
+};
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs;
+static std::vector<ProfRec> g_open;
+static std::mutex g_prof_mu;
+bool prof_enabled() { return g_prof; }
+void prof_begin(int tag, int64_t units, cudaStream_t stream) {
+  ProfRec r;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  r.tag = tag;
+  r.units = units;
+  cudaEventRecord(r.a, stream);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_open.push_back(r);
+}
+void prof_end(int tag, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (size_t i = g_open.size(); i-- > 0;) {
+    if (g_open[i].tag == tag) {
+      cudaEventRecord(g_open[i].b, stream);
+      g_recs.push_back(g_open[i]);
+      g_open.erase(g_open.begin() + i);
+      return;
+    }
+  }
+}
 }  // namespace nmb
 
 extern "C" {
+void nmb_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(nmb::g_prof_mu);
+  nmb::g_prof = on != 0;
+}
+int nmb_profile_collect(double* ms, int64_t* launches, int64_t* units, int n_tags) {
+  std::lock_guard<std::mutex> lk(nmb::g_prof_mu);
+  for (int i = 0; i < n_tags; ++i) {
+    ms[i] = 0;
+    launches[i] = 0;
+    units[i] = 0;
+  }
+  for (auto& r : nmb::g_recs) {
+    cudaEventSynchronize(r.b);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    if (r.tag < n_tags) {
+      ms[r.tag] += t;
+      launches[r.tag] += 1;
+      units[r.tag] += r.units;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  nmb::g_recs.clear();
+  return 0;
+}
 const char* nmb_last_error(void) { return nmb::g_error.c_str(); }
 int nmb_version(void) { return NMB_VERSION; }
 int64_t nmb_launch_count(void) { return nmb::g_launches.load(); }

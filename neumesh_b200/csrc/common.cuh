@@ -61,4 +61,22 @@ struct DevBuf {
 
 int sm_count();
 
+// Optional per-kernel-class device timing (bench.py's roofline): CUDA events recorded on the launching stream
+// around the launches of one class.  Disabled by default (no events, no overhead).
+enum ProfTag { PROF_KNN = 0, PROF_BOUND = 1, PROF_GEO = 2, PROF_GEO_JVP = 3, PROF_COLOR = 4, PROF_SAMPLER = 5, PROF_N = 6 };
+bool prof_enabled();
+void prof_begin(int tag, int64_t units, cudaStream_t stream);
+void prof_end(int tag, cudaStream_t stream);
+struct ProfScope {
+  int tag;
+  cudaStream_t stream;
+  bool on;
+  ProfScope(int t, int64_t units, cudaStream_t s) : tag(t), stream(s), on(prof_enabled()) {
+    if (on) prof_begin(tag, units, stream);
+  }
+  ~ProfScope() {
+    if (on) prof_end(tag, stream);
+  }
+};
+
 }  // namespace nmb

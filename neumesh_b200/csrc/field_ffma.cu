@@ -233,6 +233,7 @@ static int launch_ffma(const nmb_field* f, const MlpFfma& mlp, const FieldIn& in
   }
   const int64_t tiles = ceil_div(P, PTS);
   const int64_t grid = tiles < (int64_t)2 * sm_count() ? tiles : (int64_t)2 * sm_count();
+  ProfScope prof(MODE == 2 ? PROF_COLOR : (MODE == 1 ? PROF_GEO_JVP : PROF_GEO), P, stream);
   mlp_ffma_kernel<MODE><<<(unsigned)grid, FT, smem, stream>>>(prm);
   NMB_LAUNCH_OK();
   return 0;

@@ -498,6 +498,7 @@ knn_distance_kernel(const float4* __restrict__ nodes, const float4* __restrict__
 int launch_knn_distance(const nmb_grid* g, const float4* indicator_sorted, float w1, PointSrc src, int64_t P,
                         KnnOut out, cudaStream_t stream) {
   if (P <= 0) return 0;
+  ProfScope prof(PROF_KNN, P, stream);
   knn_distance_kernel<<<(unsigned)ceil_div(P, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src,
                                                                       P, out);
   NMB_LAUNCH_OK();
@@ -537,6 +538,7 @@ int launch_bound_scan(const nmb_grid* g, const float4* indicator, float w1, cons
                       int32_t* bfar, cudaStream_t stream) {
   const int64_t n = R * n_grid;
   if (n <= 0) return 0;
+  ProfScope prof(PROF_BOUND, n, stream);
   bound_scan_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator, w1, rays_o, dirs,
                                                                     near, far, R, n_grid, thresh, bnear, bfar);
   NMB_LAUNCH_OK();

@@ -165,7 +165,8 @@ class NeuMesh(nn.Module):
         return self._field
 
     def _release_field(self):
-        h, self._field = self._field, None
+        h = self.__dict__.get("_field")
+        self.__dict__["_field"] = None   # plain attribute: bypass nn.Module.__setattr__ (safe at interpreter exit)
         if h:
             try:
                 _lib.lib().nmb_field_destroy(h)

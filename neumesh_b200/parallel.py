@@ -62,3 +62,10 @@ def render_sharded(rays_o, rays_d, model, **render_kwargs):
     lo, hi = shard_range(n, rank, world)
     part = render_fused(rays_o.reshape(-1, 3)[lo:hi], rays_d.reshape(-1, 3)[lo:hi], model, **render_kwargs)
     return gather_image(part, n, rank, world)
+
+
+def render_sharded_local(o_part, d_part, model, n_rays, rank, world, **render_kwargs):
+    """As ``render_sharded`` when the caller already holds only this rank's slice of the rays."""
+    from .renderer import render_fused
+    part = render_fused(o_part, d_part, model, **render_kwargs)
+    return gather_image(part, n_rays, rank, world)
