@@ -38,17 +38,21 @@ constexpr int NB = 4;                      // B ring slots (loader -> MMA)
 // NOTE two separate A rings: an mbarrier parity wait is only meaningful while the waiter is at most one phase
 // ahead of the barrier.  The builder runs a whole tile ahead of the epilogue, so the two producer groups must not
 // share one ring (a shared ring deadlocks as soon as a CTA processes a second tile).
-constexpr int N_EPI = 128, N_BUILD = 128;
+constexpr int N_EPI = 256;                 // 2 groups x 4 warps: group g drains the 16-column chunks j with j % 2 == g
+constexpr int N_BUILD = 128;
 constexpr int THREADS = N_EPI + N_BUILD + 64;
-constexpr int SIG_BUF = 64 * 17;           // floats per sigma' exchange buffer (64 rows x 16 cols, padded)
+constexpr int WARP_BUILD = N_EPI / 32, WARP_MMA = (N_EPI + N_BUILD) / 32;
+constexpr int SIG_BUF = 64 * 16;           // floats per exp(100 z) exchange buffer (64 value rows x 16 columns)
 
 struct SmemLayout {
   static constexpr int a_off = 0;
   static constexpr int b_off = NA * A_SLOT;
-  static constexpr int sig_off = b_off + NB * B_SLOT;
-  static constexpr int bar_off = sig_off + 2 * SIG_BUF * 4;
+  static constexpr int sig_off = b_off + NB * B_SLOT;          // [group][parity] buffers
+  static constexpr int part_off = sig_off + 4 * SIG_BUF * 4;   // last-layer partial sums of group 1: [3][128]
+  static constexpr int bar_off = part_off + 3 * ROWS * 4;
   static constexpr int total = bar_off + 256;
 };
+static_assert(SmemLayout::total <= 232448, "shared memory budget");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -122,6 +126,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -174,8 +184,8 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
   char* a_ring = smem + SmemLayout::a_off;
   char* b_ring = smem + SmemLayout::b_off;
   float* sig = reinterpret_cast<float*>(smem + SmemLayout::sig_off);
+  float* part = reinterpret_cast<float*>(smem + SmemLayout::part_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SmemLayout::bar_off);
-  // barrier indices
   // A_FULL / A_EMPTY: slots [0, NA0) belong to the first-layer ring, [NA0, NA) to the hidden-layer ring
   constexpr int A_FULL = 0, A_EMPTY = NA, B_FULL = 2 * NA, B_EMPTY = 2 * NA + NB, D_FULL = 2 * NA + 2 * NB,
                 D_EMPTY = D_FULL + 2, N_BARS = D_EMPTY + 2;
@@ -186,6 +196,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   constexpr int PTS = (MODE == 1) ? 64 : 128;
+  constexpr int N_CHUNK = MLP_W / SLAB_K;
   const int64_t n_tiles = (prm.P + PTS - 1) / PTS;
   const FieldLayout& L = prm.lay;
   const int NL = prm.n_layers;
@@ -201,11 +212,11 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(D_FULL + i), 1);
-      mbar_init(bar(D_EMPTY + i), 128);
+      mbar_init(bar(D_EMPTY + i), N_EPI);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
                  "r"(512u)
                  : "memory");
@@ -216,12 +227,16 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp < 4) {
+  if (warp < WARP_BUILD) {
     // =========================================== epilogue ===========================================
-    const int r = tid;                         // row == TMEM lane
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int grp = warp >> 2;                 // 0 / 1: which half of the chunks this warp-group drains
+    const int r = tid & 127;                   // row == TMEM lane (warp % 4 selects the lane quadrant)
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    float* sig_g = sig + grp * 2 * SIG_BUF;
     uint32_t g = 0;                            // global layer counter of this CTA
     uint32_t it = 0;                           // tile iteration of this CTA
+    constexpr float K_EXP = 144.26950408889634f;       // 100 * log2(e)
+    constexpr float K_LOG = 0.0069314718055994531f;    // ln(2) / 100
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int64_t p = tile * PTS + ((MODE == 1) ? (r & 63) : r);
       const bool valid = p < prm.P;
@@ -235,32 +250,55 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
         const bool last = (l == NL - 1);
         float o0 = 0.f, o1 = 0.f, o2 = 0.f;
 #pragma unroll 1
-        for (int j = 0; j < MLP_W / SLAB_K; ++j) {
+        for (int j = grp; j < N_CHUNK; j += 2) {
           float v[16];
           tmem_ld16(tmem_base + lane_base + buf * 256u + (uint32_t)(j * SLAB_K), v);
           if (MODE == 2) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(bl + j * 16 + i), 0.f);
-          } else if (MODE == 0 || r < 64) {
-            if (MODE == 1) {
-              float* sb = sig + (j & 1) * SIG_BUF + r * 17;
+          } else if (MODE == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float z = v[i] + __ldg(bl + j * 16 + i);
+              const float a = z * 100.f;
+              const float y = __log2f(1.0f + fast_exp2(z * K_EXP)) * K_LOG;
+              v[i] = a > 20.f ? z : y;
+            }
+          } else {
+            // MODE 1: value rows (0..63) publish e = exp(100 z); both halves then work in parallel:
+            // value: softplus = log(1 + e) / 100, tangent: sigma'(z) * (W t) with sigma' = e / (1 + e)
+            float* sb = sig_g + ((j >> 1) & 1) * SIG_BUF;
+            float e[16];
+            if (r < 64) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const float z = v[i] + __ldg(bl + j * 16 + i);
-                sb[i] = softplus100_grad(z);
-                v[i] = softplus100(z);
+                v[i] = v[i] + __ldg(bl + j * 16 + i);
+                e[i] = fast_exp2(v[i] * K_EXP);
+              }
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<float4*>(sb + r * 16 + c * 4) = make_float4(e[c * 4], e[c * 4 + 1], e[c * 4 + 2], e[c * 4 + 3]);
+            }
+            if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+            else asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (r < 64) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float y = __log2f(1.0f + e[i]) * K_LOG;
+                v[i] = (v[i] * 100.f > 20.f) ? v[i] : y;
               }
             } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = softplus100(v[i] + __ldg(bl + j * 16 + i));
-            }
-          }
-          if (MODE == 1) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (r >= 64) {
-              const float* sb = sig + (j & 1) * SIG_BUF + (r - 64) * 17;
+              for (int c = 0; c < 4; ++c) {
+                const float4 ev = *reinterpret_cast<const float4*>(sb + (r - 64) * 16 + c * 4);
+                const float ee[4] = {ev.x, ev.y, ev.z, ev.w};
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] *= sb[i];  // sigma'(z) * (W t)
+                for (int i = 0; i < 4; ++i) {
+                  // 100 z > 20  <=>  e > exp(20)
+                  const float sg = ee[i] > 485165195.4097903f ? 1.f : __fdividef(ee[i], ee[i] + 1.f);
+                  v[c * 4 + i] *= sg;
+                }
+              }
             }
           }
           if (!last) {
@@ -285,23 +323,43 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
         tc_fence_before();
         mbar_arrive(bar(D_EMPTY + buf));
         if (!last) {
-          q += MLP_W / SLAB_K;
-        } else if (valid) {
-          if (MODE == 2) {
-            prm.out0[0 * prm.in.stride + p] = sigmoid_acc(o0 + __ldg(prm.b_out + 0));
-            prm.out0[1 * prm.in.stride + p] = sigmoid_acc(o1 + __ldg(prm.b_out + 1));
-            prm.out0[2 * prm.in.stride + p] = sigmoid_acc(o2 + __ldg(prm.b_out + 2));
-          } else if (MODE == 0 || r < 64) {
-            prm.out0[p] = o0 + __ldg(prm.b_out);
-          } else if (prm.out1) {
-            prm.out1[0 * prm.in.stride + p] = o0 * prm.in.grad[0 * prm.in.stride + p];
-            prm.out1[1 * prm.in.stride + p] = o0 * prm.in.grad[1 * prm.in.stride + p];
-            prm.out1[2 * prm.in.stride + p] = o0 * prm.in.grad[2 * prm.in.stride + p];
+          q += N_CHUNK;
+        } else {
+          // combine the two groups' partial dot products (group 1 -> smem -> group 0)
+          if (grp == 1) {
+            part[r] = o0;
+            if (MODE == 2) {
+              part[ROWS + r] = o1;
+              part[2 * ROWS + r] = o2;
+            }
           }
+          asm volatile("bar.sync 3, 256;" ::: "memory");
+          if (grp == 0) {
+            o0 += part[r];
+            if (MODE == 2) {
+              o1 += part[ROWS + r];
+              o2 += part[2 * ROWS + r];
+            }
+            if (valid) {
+              if (MODE == 2) {
+                prm.out0[0 * prm.in.stride + p] = sigmoid_acc(o0 + __ldg(prm.b_out + 0));
+                prm.out0[1 * prm.in.stride + p] = sigmoid_acc(o1 + __ldg(prm.b_out + 1));
+                prm.out0[2 * prm.in.stride + p] = sigmoid_acc(o2 + __ldg(prm.b_out + 2));
+              } else if (MODE == 0 || r < 64) {
+                prm.out0[p] = o0 + __ldg(prm.b_out);
+              } else if (prm.out1) {
+                prm.out1[0 * prm.in.stride + p] = o0 * prm.in.grad[0 * prm.in.stride + p];
+                prm.out1[1 * prm.in.stride + p] = o0 * prm.in.grad[1 * prm.in.stride + p];
+                prm.out1[2 * prm.in.stride + p] = o0 * prm.in.grad[2 * prm.in.stride + p];
+              }
+            }
+          }
+          // group 1 may only overwrite `part` after group 0 has read it
+          asm volatile("bar.sync 4, 256;" ::: "memory");
         }
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < WARP_MMA) {
     // =========================================== builder ============================================
     const int r = tid - N_EPI;
     uint32_t it = 0;
@@ -393,7 +451,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
         fr *= 2.f;
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == WARP_MMA) {
     // =========================================== MMA issuer =========================================
     if ((tid & 31) == 0) {
       uint32_t g = 0, q = 0, q0 = 0, q1 = 0;   // q: B ring; q0 / q1: first-layer / hidden-layer A rings
@@ -460,7 +518,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == WARP_MMA) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }

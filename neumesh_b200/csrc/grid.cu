@@ -161,15 +161,79 @@ __global__ void lvl_boxes_kernel(int32_t first_node, int32_t n_nodes, const int3
   } else {  // internal: union of the (already final) child boxes
     int32_t lc = nlast[n];
     for (int32_t c = fc; c <= lc; ++c) {
-      float4 a = nodes[2 * c], b = nodes[2 * c + 1];
+      float4 a = nodes[NODE_F4 * c], b = nodes[NODE_F4 * c + 1];
       lo.x = fminf(lo.x, a.x); lo.y = fminf(lo.y, a.y); lo.z = fminf(lo.z, a.z);
       hi.x = fmaxf(hi.x, b.x); hi.y = fmaxf(hi.y, b.y); hi.z = fmaxf(hi.z, b.z);
     }
     link = __int_as_float(fc);
     cnt = __int_as_float(lc - fc + 1);
   }
-  nodes[2 * n] = make_float4(lo.x, lo.y, lo.z, link);
-  nodes[2 * n + 1] = make_float4(hi.x, hi.y, hi.z, cnt);
+  nodes[NODE_F4 * n] = make_float4(lo.x, lo.y, lo.z, link);
+  nodes[NODE_F4 * n + 1] = make_float4(hi.x, hi.y, hi.z, cnt);
+
+  // ---- disc bound: centre c, radius r, axis u, half-thickness t (see knn_walk) ----
+  const int32_t b = nbegin[n], e = nend[n];
+  const int32_t cntp = e - b;
+  float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);
+  float ux = 0.f, uy = 0.f, uz = 1.f, r, th;
+  if (cntp > DISC_MAX_POINTS) {
+    const float ex = hi.x - cx, ey = hi.y - cy, ez = hi.z - cz;
+    r = sqrtf(ex * ex + ey * ey + ez * ez);
+    th = r;
+  } else {
+    // centroid
+    double sx = 0, sy = 0, sz = 0;
+    for (int32_t i = b; i < e; ++i) {
+      const float4 p = pts[i];
+      sx += p.x; sy += p.y; sz += p.z;
+    }
+    cx = (float)(sx / cntp); cy = (float)(sy / cntp); cz = (float)(sz / cntp);
+    // covariance
+    float a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
+    for (int32_t i = b; i < e; ++i) {
+      const float4 p = pts[i];
+      const float dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
+      a00 += dx * dx; a01 += dx * dy; a02 += dx * dz; a11 += dy * dy; a12 += dy * dz; a22 += dz * dz;
+    }
+    // smallest-variance axis = dominant eigenvector of (trace * I - A): power iteration from 3 starts
+    const float tr = a00 + a11 + a22;
+    if (tr > 0.f) {
+      const float m00 = tr - a00, m11 = tr - a11, m22 = tr - a22;
+      float best = -1.f;
+      for (int s0 = 0; s0 < 3; ++s0) {
+        float vx = s0 == 0, vy = s0 == 1, vz = s0 == 2;
+        for (int it = 0; it < 24; ++it) {
+          const float wx = m00 * vx - a01 * vy - a02 * vz;
+          const float wy = -a01 * vx + m11 * vy - a12 * vz;
+          const float wz = -a02 * vx - a12 * vy + m22 * vz;
+          const float nn = sqrtf(wx * wx + wy * wy + wz * wz);
+          if (!(nn > 0.f)) break;
+          vx = wx / nn; vy = wy / nn; vz = wz / nn;
+        }
+        // Rayleigh quotient of (trace I - A): larger is better
+        const float q = vx * (m00 * vx - a01 * vy - a02 * vz) + vy * (-a01 * vx + m11 * vy - a12 * vz) +
+                        vz * (-a02 * vx - a12 * vy + m22 * vz);
+        if (q > best) {
+          best = q; ux = vx; uy = vy; uz = vz;
+        }
+      }
+      const float un = sqrtf(ux * ux + uy * uy + uz * uz);
+      if (un > 0.5f) { ux /= un; uy /= un; uz /= un; } else { ux = 0.f; uy = 0.f; uz = 1.f; }
+    }
+    r = 0.f;
+    th = 0.f;
+    for (int32_t i = b; i < e; ++i) {
+      const float4 p = pts[i];
+      const float dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
+      r = fmaxf(r, sqrtf(dx * dx + dy * dy + dz * dz));
+      th = fmaxf(th, fabsf(ux * dx + uy * dy + uz * dz));
+    }
+  }
+  // inflate: the bound is evaluated in fp32 and must never exceed the true distance to any point of the node
+  r = r * 1.00001f + 1e-7f;
+  th = th * 1.00001f + 1e-7f;
+  nodes[NODE_F4 * n + 2] = make_float4(cx, cy, cz, r);
+  nodes[NODE_F4 * n + 3] = make_float4(ux, uy, uz, th);
 }
 
 static int build_grid(const float* vertices, int64_t V, cudaStream_t stream, nmb_grid* g) {
@@ -293,7 +357,7 @@ static int build_grid(const float* vertices, int64_t V, cudaStream_t stream, nmb
     lvl_off.push_back(n_nodes);
   }
   g->num_nodes = n_nodes;
-  NMB_CUDA_OK(g->nodes.alloc(2 * (int64_t)n_nodes));
+  NMB_CUDA_OK(g->nodes.alloc(NODE_F4 * (int64_t)n_nodes));
   for (int l = (int)lvl_off.size() - 2; l >= 0; --l) {
     const int32_t first = lvl_off[l], cnt = lvl_off[l + 1] - lvl_off[l];
     if (cnt <= 0) continue;
@@ -320,6 +384,27 @@ __device__ __forceinline__ float box_dist_rn(float qx, float qy, float qz, const
   const float dy = fmaxf(fmaxf(__fsub_rn(lo.y, qy), __fsub_rn(qy, hi.y)), 0.f);
   const float dz = fmaxf(fmaxf(__fsub_rn(lo.z, qz), __fsub_rn(qz, hi.z)), 0.f);
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// Lower bound of sq_dist_rn(q, p) over the points p of a node, from its two bounding volumes:
+//  * the tight axis-aligned box (exact-safe: rounding is monotone), and
+//  * a "disc": all points satisfy |p - c| <= r and |u . (p - c)| <= t, hence with a = u . (q - c) and
+//    b = sqrt(|q - c|^2 - a^2):  dist^2 >= max(|a| - t, 0)^2 + max(b - r, 0)^2.
+// A mesh is locally a thin sheet (t << r), so for a query FAR from the surface the disc bound is within ~t of the true
+// distance while the box bound is short by up to the box size; the number of nodes that survive pruning drops from
+// ~2*pi*D/size per level to a handful.  The disc value is deflated a little so that fp32 rounding can never make it
+// exceed a true distance (r and t are inflated at build time as well).
+__device__ __forceinline__ float node_bound(float qx, float qy, float qz, const float4& lo, const float4& hi,
+                                            const float4& cr, const float4& ut) {
+  const float bd = box_dist_rn(qx, qy, qz, lo, hi);
+  const float dx = qx - cr.x, dy = qy - cr.y, dz = qz - cr.z;
+  const float a = ut.x * dx + ut.y * dy + ut.z * dz;
+  const float dd = dx * dx + dy * dy + dz * dz;
+  const float b = sqrtf(fmaxf(dd - a * a, 0.f));
+  const float h = fmaxf(fabsf(a) - ut.w, 0.f);
+  const float l = fmaxf(b - cr.w, 0.f);
+  const float disc = (h * h + l * l) * 0.99998f - 1e-12f;
+  return fmaxf(bd, disc);
 }
 
 // Insert (nd, ni) into the ascending list d[0..K-1] (precondition nd < d[K-1]); branch-free, strict '<' keeps
@@ -372,8 +457,8 @@ __device__ __forceinline__ void knn_walk(const float4* __restrict__ nodes, const
     --sp;
     const int32_t n = sn[sp];
     if (sd[sp] >= d[K - 1]) continue;
-    const float4 a = __ldg(&nodes[2 * n]);
-    const float4 b = __ldg(&nodes[2 * n + 1]);
+    const float4 a = __ldg(&nodes[NODE_F4 * n]);
+    const float4 b = __ldg(&nodes[NODE_F4 * n + 1]);
     const int32_t link = __float_as_int(a.w);
     const int32_t cnt = __float_as_int(b.w);
     if (cnt < 0) {
@@ -392,9 +477,8 @@ __device__ __forceinline__ void knn_walk(const float4* __restrict__ nodes, const
         cd[c] = CUDART_INF_F;
         cn[c] = link + c;
         if (c < cnt) {
-          const float4 lo = __ldg(&nodes[2 * (link + c)]);
-          const float4 hi = __ldg(&nodes[2 * (link + c) + 1]);
-          const float bd = box_dist_rn(qx, qy, qz, lo, hi);
+          const float4* nc = nodes + NODE_F4 * (link + c);
+          const float bd = node_bound(qx, qy, qz, __ldg(nc), __ldg(nc + 1), __ldg(nc + 2), __ldg(nc + 3));
           cd[c] = bd < worst ? bd : CUDART_INF_F;
         }
       }
@@ -567,8 +651,8 @@ knn_generic_kernel(const float4* __restrict__ nodes, const float4* __restrict__ 
     --sp;
     const int32_t n = sn[sp];
     if (sd[sp] >= d[K - 1]) continue;
-    const float4 a = __ldg(&nodes[2 * n]);
-    const float4 b = __ldg(&nodes[2 * n + 1]);
+    const float4 a = __ldg(&nodes[NODE_F4 * n]);
+    const float4 b = __ldg(&nodes[NODE_F4 * n + 1]);
     const int32_t link = __float_as_int(a.w);
     const int32_t cnt = __float_as_int(b.w);
     if (cnt < 0) {
@@ -592,7 +676,8 @@ knn_generic_kernel(const float4* __restrict__ nodes, const float4* __restrict__ 
       for (int c = 0; c < 8; ++c) {
         cd[c] = -1.f;
         if (c < cnt) {
-          const float bd = box_dist_rn(qx, qy, qz, __ldg(&nodes[2 * (link + c)]), __ldg(&nodes[2 * (link + c) + 1]));
+          const float4* nc = nodes + NODE_F4 * (link + c);
+          const float bd = node_bound(qx, qy, qz, __ldg(nc), __ldg(nc + 1), __ldg(nc + 2), __ldg(nc + 3));
           if (bd < d[K - 1]) cd[c] = bd;
         }
       }

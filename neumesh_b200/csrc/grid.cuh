@@ -11,13 +11,15 @@ struct nmb_grid {
   nmb::DevBuf<float4> pts;     // [V] sorted by Morton code: x, y, z, __int_as_float(original index)
   nmb::DevBuf<int32_t> order;  // [V] sorted slot -> original index
   nmb::DevBuf<int32_t> inv;    // [V] original index -> sorted slot
-  nmb::DevBuf<float4> nodes;   // [2*num_nodes]: {lo.xyz, link}, {hi.xyz, count}; see grid.cu
+  nmb::DevBuf<float4> nodes;   // [NODE_F4*num_nodes]: box + disc bounds and child / point links; see grid.cu
 };
 
 namespace nmb {
 
 constexpr int KNN_K = 8;          // neighbours used by the field (mesh_grid.py:77 default K=8)
 constexpr int LEAF_MAX = 8;       // nodes with <= LEAF_MAX points are leaves
+constexpr int NODE_F4 = 4;        // float4 per node: {lo, link}, {hi, count}, {centre, r}, {axis, t}
+constexpr int DISC_MAX_POINTS = 8192;  // nodes larger than this get the trivial disc (sphere) bound
 constexpr int STACK_MAX = 96;     // traversal stack entries (7 * depth + 8 <= 78 for depth 10)
 
 // Per-point outputs of the fused KNN + mesh-distance kernel, structure-of-arrays with stride `stride`

@@ -41,8 +41,12 @@ def mesh_distance(xyz: torch.Tensor, vertices: torch.Tensor, indicator: torch.Te
     """``MeshGrid.compute_distance_frnn`` (models/mesh_grid.py:88-144).
 
     xyz [M,3] -> ds [M,1] (differentiable in xyz / indicator / w1), idx [M,K] int64, w [M,K] (detached).
+    In float64 ("truth" mode of the tests) the neighbours are still the fp32 selection; their distances are then
+    re-evaluated in float64.
     """
     d2, idx = _knn.knn_exact(xyz, vertices, K)
+    if xyz.dtype == torch.float64:
+        d2 = ((xyz.detach()[:, None, :] - vertices[idx]) ** 2).sum(-1)
     dist = d2.sqrt()  # mesh_grid.py:123
     w = 1.0 / (dist + 1e-7)  # :124
     w = w / w.sum(dim=-1, keepdim=True)  # :125
@@ -56,10 +60,13 @@ def mesh_distance(xyz: torch.Tensor, vertices: torch.Tensor, indicator: torch.Te
 class FieldOracle:
     """The NeuMesh model protocol the renderer uses, over a raw ``state_dict``."""
 
-    def __init__(self, vertices, state_dict, cfg):
+    def __init__(self, vertices, state_dict, cfg, dtype=torch.float32):
+        """``dtype=torch.float64`` evaluates the same fp32 parameters in double precision: the "truth" against which
+        the tests measure how accurate each fp32 implementation (this oracle, the CUDA kernels) is."""
         self.cfg = cfg
-        self.vertices = torch.as_tensor(vertices, dtype=torch.float32).contiguous()
-        self.p = {k: v.detach().clone().float() for k, v in state_dict.items()}
+        self.dtype = dtype
+        self.vertices = torch.as_tensor(vertices, dtype=torch.float32).to(dtype).contiguous()
+        self.p = {k: v.detach().clone().float().to(dtype) for k, v in state_dict.items()}
         self.speed_factor = cfg.speed_factor
         self.enable_nablas_input = cfg.enable_nablas_input
 

@@ -31,9 +31,9 @@ def golden_case(path):
     return g, mesh, cfg, sd, kw
 
 
-def oracle_field(mesh, cfg, sd):
+def oracle_field(mesh, cfg, sd, dtype=torch.float32):
     from oracle.field import FieldOracle
-    return FieldOracle(mesh.vertices, sd, cfg)
+    return FieldOracle(mesh.vertices, sd, cfg, dtype=dtype)
 
 
 def cuda_model(mesh, cfg, sd, engine="tcgen05", device="cuda:0"):
