@@ -17,6 +17,7 @@
 // Operand layout (no-swizzle, K-major "interleave" canonical layout): a K-slab of 16 columns is stored as
 // [k/4][row][k%4] fp32, i.e. 8x16-byte core matrices with SBO = 128 B (next 8 rows) and LBO = rows*16 B (next 4 k).
 // Weights are pre-packed in exactly this image (hi slab then lo slab) so a slab is ONE contiguous 32 KB bulk copy.
+#include <cstdlib>
 #include <vector>
 
 #include "field_build.cuh"
@@ -32,24 +33,27 @@ constexpr int A_SLOT = 2 * A_HALF;         // 16 KB
 constexpr int B_HALF = MLP_W * SLAB_K * 4; // 16 KB
 constexpr int B_SLOT = 2 * B_HALF;         // 32 KB
 constexpr int NA0 = 2;                     // first-layer A ring (builder -> MMA)
-constexpr int NA1 = 3;                     // hidden-layer A ring (epilogue -> MMA)
+constexpr int NA1 = 4;                     // hidden-layer A ring (epilogue -> MMA)
 constexpr int NA = NA0 + NA1;
-constexpr int NB = 4;                      // B ring slots (loader -> MMA)
+constexpr int NB = 3;                      // B ring slots (loader -> MMA)
+constexpr int CLUSTER = 2;                 // CTAs per cluster sharing every weight slab through TMA multicast
 // NOTE two separate A rings: an mbarrier parity wait is only meaningful while the waiter is at most one phase
 // ahead of the barrier.  The builder runs a whole tile ahead of the epilogue, so the two producer groups must not
 // share one ring (a shared ring deadlocks as soon as a CTA processes a second tile).
 constexpr int N_EPI = 256;                 // 2 groups x 4 warps: group g drains the 16-column chunks j with j % 2 == g
-constexpr int N_BUILD = 128;
+constexpr int N_BUILD = 256;               // 2 threads per row: half h builds columns [8h, 8h+8) of every first-layer slab
 constexpr int THREADS = N_EPI + N_BUILD + 64;
 constexpr int WARP_BUILD = N_EPI / 32, WARP_MMA = (N_EPI + N_BUILD) / 32;
 constexpr int SIG_BUF = 64 * 16;           // floats per exp(100 z) exchange buffer (64 value rows x 16 columns)
+constexpr int CONST_FLOATS = (MAX_LAYERS + 3) * MLP_W;   // biases of every hidden layer + up to 3 output rows
 
 struct SmemLayout {
   static constexpr int a_off = 0;
   static constexpr int b_off = NA * A_SLOT;
   static constexpr int sig_off = b_off + NB * B_SLOT;          // [group][parity] buffers
   static constexpr int part_off = sig_off + 4 * SIG_BUF * 4;   // last-layer partial sums of group 1: [3][128]
-  static constexpr int bar_off = part_off + 3 * ROWS * 4;
+  static constexpr int const_off = part_off + 3 * ROWS * 4;    // biases + output weights
+  static constexpr int bar_off = const_off + CONST_FLOATS * 4;
   static constexpr int total = bar_off + 256;
 };
 static_assert(SmemLayout::total <= 232448, "shared memory budget");
@@ -77,6 +81,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// single-thread roles (MMA issuer, loader): back off between polls so the spin does not steal issue slots from the
+// epilogue / builder warps that share the scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(40);
+  }
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -85,6 +105,30 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+
+// Multicast variant: the bytes land at the same CTA-relative offset in every CTA of `mask`, and complete_tx is
+// signalled on the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void bulk_load_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // UMMA shared-memory descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30),
@@ -111,6 +155,23 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+// the registers are tied to the wait ("+r") so that no consumer can be scheduled ahead of it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
@@ -156,6 +217,25 @@ __device__ __forceinline__ void store_a_row(char* a_slot, int r, const float (&v
   }
 }
 
+// write 8 consecutive K-columns [8h, 8h+8) of row `r` (two 4-column chunks) into an A slot
+__device__ __forceinline__ void store_a_half(char* a_slot, int r, int h, const float (&v)[8]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int kc = 2 * h + c;
+    float4 hi, lo;
+    hi.x = tf32_rna(v[c * 4 + 0]);
+    hi.y = tf32_rna(v[c * 4 + 1]);
+    hi.z = tf32_rna(v[c * 4 + 2]);
+    hi.w = tf32_rna(v[c * 4 + 3]);
+    lo.x = tf32_rna(v[c * 4 + 0] - hi.x);
+    lo.y = tf32_rna(v[c * 4 + 1] - hi.y);
+    lo.z = tf32_rna(v[c * 4 + 2] - hi.z);
+    lo.w = tf32_rna(v[c * 4 + 3] - hi.w);
+    *reinterpret_cast<float4*>(a_slot + kc * (ROWS * 16) + r * 16) = hi;
+    *reinterpret_cast<float4*>(a_slot + A_HALF + kc * (ROWS * 16) + r * 16) = lo;
+  }
+}
+
 struct Params {
   FieldLayout lay;
   FieldIn in;
@@ -171,20 +251,43 @@ struct Params {
   int64_t P;
   float* out0;
   float* out1;
+  unsigned long long* dbg;   // optional [8] cycle counters (NMB_TC_PROFILE=1): where the pipeline waits
 };
+
+// wait that accounts its cycles into `acc` when profiling
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, bool prof, unsigned long long& acc) {
+  if (!prof) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += (unsigned long long)(clock64() - t0);
+}
+__device__ __forceinline__ void mbar_wait_bt(uint32_t bar, uint32_t parity, bool prof, unsigned long long& acc) {
+  if (!prof) {
+    mbar_wait_backoff(bar, parity);
+    return;
+  }
+  const long long t0 = clock64();
+  mbar_wait_backoff(bar, parity);
+  acc += (unsigned long long)(clock64() - t0);
+}
 
 }  // namespace tc
 
 // MODE 0: geometry, 128 points / tile.  MODE 1: geometry + tangent rows (rows 64..127 carry d/d(ds) of rows 0..63).
 // MODE 2: colour, 128 points / tile.
 template <int MODE>
-__global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params prm) {
+__global__ void __cluster_dims__(tc::CLUSTER, 1, 1) __launch_bounds__(tc::THREADS, 1)
+mlp_tc_kernel(const tc::Params prm) {
   using namespace tc;
   extern __shared__ __align__(1024) char smem[];
   char* a_ring = smem + SmemLayout::a_off;
   char* b_ring = smem + SmemLayout::b_off;
   float* sig = reinterpret_cast<float*>(smem + SmemLayout::sig_off);
   float* part = reinterpret_cast<float*>(smem + SmemLayout::part_off);
+  float* cst = reinterpret_cast<float*>(smem + SmemLayout::const_off);   // [n_layers][256] biases, then output rows
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SmemLayout::bar_off);
   // A_FULL / A_EMPTY: slots [0, NA0) belong to the first-layer ring, [NA0, NA) to the hidden-layer ring
   constexpr int A_FULL = 0, A_EMPTY = NA, B_FULL = 2 * NA, B_EMPTY = 2 * NA + NB, D_FULL = 2 * NA + 2 * NB,
@@ -197,24 +300,32 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
   const int warp = tid >> 5;
   constexpr int PTS = (MODE == 1) ? 64 : 128;
   constexpr int N_CHUNK = MLP_W / SLAB_K;
-  const int64_t n_tiles = (prm.P + PTS - 1) / PTS;
+  const int64_t n_tiles_real = (prm.P + PTS - 1) / PTS;
+  // every CTA runs the SAME number of tiles (padding with all-invalid tiles): the CTAs of a cluster consume the
+  // weight-slab stream in lock step, so none may stop early
+  const int64_t n_tiles = ((n_tiles_real + gridDim.x - 1) / gridDim.x) * gridDim.x;
   const FieldLayout& L = prm.lay;
   const int NL = prm.n_layers;
 
   if (tid == 0) {
     for (int i = 0; i < NA; ++i) {
-      mbar_init(bar(A_FULL + i), 128);
+      mbar_init(bar(A_FULL + i), i < NA0 ? N_BUILD : 128);   // first-layer slabs: both half-row builders arrive
       mbar_init(bar(A_EMPTY + i), 1);
     }
     for (int i = 0; i < NB; ++i) {
       mbar_init(bar(B_FULL + i), 1);
-      mbar_init(bar(B_EMPTY + i), 1);
+      mbar_init(bar(B_EMPTY + i), CLUSTER);   // released by the MMA warps of every CTA in the cluster
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(D_FULL + i), 1);
       mbar_init(bar(D_EMPTY + i), N_EPI);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {
+    const int n_out = (MODE == 2) ? 3 : 1;
+    for (int i = tid; i < prm.n_layers * MLP_W; i += THREADS) cst[i] = prm.bias[i];
+    for (int i = tid; i < n_out * MLP_W; i += THREADS) cst[prm.n_layers * MLP_W + i] = prm.w_out[i];
   }
   if (warp == WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
@@ -223,7 +334,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();   // barriers of every CTA in the cluster are initialised before any multicast can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -235,6 +346,9 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
     float* sig_g = sig + grp * 2 * SIG_BUF;
     uint32_t g = 0;                            // global layer counter of this CTA
     uint32_t it = 0;                           // tile iteration of this CTA
+    const bool prof = prm.dbg != nullptr;
+    unsigned long long t_dfull = 0, t_aempty = 0;
+    const long long t_begin = clock64();
     constexpr float K_EXP = 144.26950408889634f;       // 100 * log2(e)
     constexpr float K_LOG = 0.0069314718055994531f;    // ln(2) / 100
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -244,22 +358,29 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
       uint32_t q = it * (uint32_t)(prm.slabs_per_tile - prm.n_slabs[0]);
       for (int l = 0; l < NL; ++l, ++g) {
         const uint32_t buf = g & 1u;
-        mbar_wait(bar(D_FULL + buf), (g >> 1) & 1u);
+        mbar_wait_t(bar(D_FULL + buf), (g >> 1) & 1u, prof, t_dfull);
         tc_fence_after();
-        const float* __restrict__ bl = prm.bias + l * MLP_W;
+        const float* bl = cst + l * MLP_W;
         const bool last = (l == NL - 1);
         float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+        // software-pipelined TMEM reads: the load of this group's NEXT chunk is in flight while the current one is
+        // being activated / split / stored
+        uint32_t raw[16];
+        tmem_ld16_issue(tmem_base + lane_base + buf * 256u + (uint32_t)(grp * SLAB_K), raw);
 #pragma unroll 1
         for (int j = grp; j < N_CHUNK; j += 2) {
           float v[16];
-          tmem_ld16(tmem_base + lane_base + buf * 256u + (uint32_t)(j * SLAB_K), v);
+          tmem_ld_wait(raw);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
+          if (j + 2 < N_CHUNK) tmem_ld16_issue(tmem_base + lane_base + buf * 256u + (uint32_t)((j + 2) * SLAB_K), raw);
           if (MODE == 2) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(bl + j * 16 + i), 0.f);
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + bl[j * 16 + i], 0.f);
           } else if (MODE == 0) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float z = v[i] + __ldg(bl + j * 16 + i);
+              const float z = v[i] + bl[j * 16 + i];
               const float a = z * 100.f;
               const float y = __log2f(1.0f + fast_exp2(z * K_EXP)) * K_LOG;
               v[i] = a > 20.f ? z : y;
@@ -272,7 +393,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
             if (r < 64) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                v[i] = v[i] + __ldg(bl + j * 16 + i);
+                v[i] = v[i] + bl[j * 16 + i];
                 e[i] = fast_exp2(v[i] * K_EXP);
               }
 #pragma unroll
@@ -304,18 +425,18 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
           if (!last) {
             const uint32_t qs = q + (uint32_t)j;
             const uint32_t slot = NA0 + qs % NA1;
-            mbar_wait(bar(A_EMPTY + slot), ((qs / NA1) & 1u) ^ 1u);
+            mbar_wait_t(bar(A_EMPTY + slot), ((qs / NA1) & 1u) ^ 1u, prof, t_aempty);
             store_a_row(a_ring + slot * A_SLOT, r, v);
             fence_proxy_async();
             mbar_arrive(bar(A_FULL + slot));
           } else {
-            const float* __restrict__ wo = prm.w_out + j * 16;
+            const float* wo = cst + NL * MLP_W + j * 16;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              o0 = fmaf(v[i], __ldg(wo + i), o0);
+              o0 = fmaf(v[i], wo[i], o0);
               if (MODE == 2) {
-                o1 = fmaf(v[i], __ldg(wo + MLP_W + i), o1);
-                o2 = fmaf(v[i], __ldg(wo + 2 * MLP_W + i), o2);
+                o1 = fmaf(v[i], wo[MLP_W + i], o1);
+                o2 = fmaf(v[i], wo[2 * MLP_W + i], o2);
               }
             }
           }
@@ -359,39 +480,57 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
         }
       }
     }
+    if (prof && (tid & 31) == 0) {
+      atomicAdd(prm.dbg + 0, t_dfull);
+      atomicAdd(prm.dbg + 1, t_aempty);
+      atomicAdd(prm.dbg + 2, (unsigned long long)(clock64() - t_begin));
+    }
   } else if (warp < WARP_MMA) {
     // =========================================== builder ============================================
-    const int r = tid - N_EPI;
+    // two threads per row: half h owns features {8g + 4h + i : g < 4, i < 4} and writes columns [8h, 8h+8) of
+    // every first-layer slab (see tc_first_layer_map for the column order)
+    const int tb = tid - N_EPI;
+    const int r = tb & (ROWS - 1);
+    const int h = tb >> 7;
     uint32_t it = 0;
     const int off_feat = (MODE == 2) ? L.off_ft : L.off_fg;   // multiple of 16
     const int Lf = (MODE == 2) ? L.Lft : L.Lfg;
+    const float* __restrict__ table = (MODE == 2) ? prm.tab.fc : prm.tab.fg;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int64_t p = tile * PTS + ((MODE == 1) ? (r & 63) : r);
       const bool valid = p < prm.P;
       const bool tangent = (MODE == 1) && (r >= 64);
       uint32_t q = it * (uint32_t)prm.n_slabs[0];   // first-layer ring counter
-      auto emit = [&](const float (&v)[16]) {
+      auto emit = [&](const float (&v)[8]) {
         const uint32_t slot = q % NA0;
         mbar_wait(bar(A_EMPTY + slot), ((q / NA0) & 1u) ^ 1u);
-        store_a_row(a_ring + slot * A_SLOT, r, v);
+        store_a_half(a_ring + slot * A_SLOT, r, h, v);
         fence_proxy_async();
         mbar_arrive(bar(A_FULL + slot));
         ++q;
       };
-      // ---- gather + blend (registers), issued before any ring wait so its latency overlaps the previous tile ----
-      float feat[FEAT];
+      // ---- gather + blend of this half's 16 features (registers); issued before any ring wait so that its
+      //      latency overlaps the previous tile ----
+      float feat[16];
 #pragma unroll
-      for (int i = 0; i < FEAT; ++i) feat[i] = 0.f;
+      for (int i = 0; i < 16; ++i) feat[i] = 0.f;
       float ds = 0.f;
       if (valid) {
         ds = prm.in.ds[p];
         if (!tangent) {
 #pragma unroll
-          for (int qq = 0; qq < 4; ++qq) {
-            float x[8];
-            blend8(MODE == 2 ? prm.tab.fc : prm.tab.fg, prm.in, p, qq, x);
+          for (int k = 0; k < KNN_K; ++k) {
+            const int32_t sl = prm.in.slot[k * prm.in.stride + p];
+            const float w = prm.in.w[k * prm.in.stride + p];
+            const float* row = table + (int64_t)sl * FEAT + 4 * h;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) feat[qq * 8 + i] = x[i];
+            for (int g4 = 0; g4 < 4; ++g4) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(row + 8 * g4));
+              feat[g4 * 4 + 0] = __fadd_rn(feat[g4 * 4 + 0], __fmul_rn(a.x, w));
+              feat[g4 * 4 + 1] = __fadd_rn(feat[g4 * 4 + 1], __fmul_rn(a.y, w));
+              feat[g4 * 4 + 2] = __fadd_rn(feat[g4 * 4 + 2], __fmul_rn(a.z, w));
+              feat[g4 * 4 + 3] = __fadd_rn(feat[g4 * 4 + 3], __fmul_rn(a.w, w));
+            }
           }
         }
       }
@@ -419,32 +558,32 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
           }
         }
         for (int s = 0; s < off_feat / SLAB_K; ++s) {
-          float v[16];
+          float v[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = head[s * 16 + i];
+          for (int i = 0; i < 8; ++i) v[i] = head[s * 16 + 8 * h + i];
           emit(v);
         }
       }
-      // ---- raw features: 2 slabs ----
+      // ---- raw features: slab s holds groups g = 2s, 2s+1: columns [8h, 8h+8) = feat[g = 2s][0..3], feat[2s+1][0..3] ----
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float v[16];
+      for (int s2 = 0; s2 < 2; ++s2) {
+        float v[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = feat[h * 16 + i];
+        for (int i = 0; i < 8; ++i) v[i] = feat[s2 * 8 + i];
         emit(v);
       }
-      // ---- bands: slab (b, h) = [sin(2^b x[8h..8h+7]), cos(2^b x[8h..8h+7])] ----
+      // ---- bands: slab (b, g): columns [8h, 8h+8) = [sin(2^b f[g][0..3]), cos(2^b f[g][0..3])] ----
       float fr = 1.f;
       for (int b = 0; b < Lf; ++b) {
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          float v[16];
+        for (int g4 = 0; g4 < 4; ++g4) {
+          float v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float s = 0.f, c = 0.f;
-            if (valid && !tangent) sincosf(feat[h * 8 + i] * fr, &s, &c);
-            v[i] = s;
-            v[8 + i] = c;
+          for (int i = 0; i < 4; ++i) {
+            float sn = 0.f, cs = 0.f;
+            if (valid && !tangent) sincosf(feat[g4 * 4 + i] * fr, &sn, &cs);
+            v[i] = sn;
+            v[4 + i] = cs;
           }
           emit(v);
         }
@@ -456,10 +595,13 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
     if ((tid & 31) == 0) {
       uint32_t g = 0, q = 0, q0 = 0, q1 = 0;   // q: B ring; q0 / q1: first-layer / hidden-layer A rings
       const uint32_t a0 = smem_u32(a_ring), b0 = smem_u32(b_ring);
+      const bool prof = prm.dbg != nullptr;
+      unsigned long long t_dempty = 0, t_a0 = 0, t_a1 = 0, t_b = 0;
+      const long long t_begin = clock64();
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int l = 0; l < NL; ++l, ++g) {
           const uint32_t buf = g & 1u;
-          mbar_wait(bar(D_EMPTY + buf), ((g >> 1) & 1u) ^ 1u);
+          mbar_wait_bt(bar(D_EMPTY + buf), ((g >> 1) & 1u) ^ 1u, prof, t_dempty);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * 256u;
           const int ns = prm.n_slabs[l];
@@ -475,8 +617,8 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
               ++q1;
             }
             const uint32_t sb = q % NB;
-            mbar_wait(bar(A_FULL + sa), pa);
-            mbar_wait(bar(B_FULL + sb), (q / NB) & 1u);
+            mbar_wait_bt(bar(A_FULL + sa), pa, prof, l == 0 ? t_a0 : t_a1);
+            mbar_wait_bt(bar(B_FULL + sb), (q / NB) & 1u, prof, t_b);
             tc_fence_after();
             const uint32_t a_addr = a0 + sa * A_SLOT, b_addr = b0 + sb * B_SLOT;
 #pragma unroll
@@ -491,10 +633,17 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
               mma_tf32(d_tmem, a_hi, b_hi, 1u);
             }
             mma_commit(bar(A_EMPTY + sa));
-            mma_commit(bar(B_EMPTY + sb));
+            mma_commit_mc(bar(B_EMPTY + sb), (uint16_t)((1u << CLUSTER) - 1u));
           }
           mma_commit(bar(D_FULL + buf));
         }
+      }
+      if (prof) {
+        atomicAdd(prm.dbg + 3, t_dempty);
+        atomicAdd(prm.dbg + 4, t_a0);
+        atomicAdd(prm.dbg + 5, t_a1);
+        atomicAdd(prm.dbg + 6, t_b);
+        atomicAdd(prm.dbg + 7, (unsigned long long)(clock64() - t_begin));
       }
     }
   } else {
@@ -502,14 +651,18 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
     if ((tid & 31) == 0) {
       uint32_t q = 0;
       const uint32_t b0 = smem_u32(b_ring);
+      const uint32_t crank = cluster_ctarank();
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         for (int l = 0; l < NL; ++l) {
           const float* src = prm.w + prm.slab_off[l];
           for (int j = 0; j < prm.n_slabs[l]; ++j, ++q) {
             const uint32_t sb = q % NB;
-            mbar_wait(bar(B_EMPTY + sb), ((q / NB) & 1u) ^ 1u);
+            mbar_wait_backoff(bar(B_EMPTY + sb), ((q / NB) & 1u) ^ 1u);
             mbar_expect_tx(bar(B_FULL + sb), B_SLOT);
-            bulk_load(b0 + sb * B_SLOT, src + (int64_t)j * (B_SLOT / 4), B_SLOT, bar(B_FULL + sb));
+            // this CTA fetches 1/CLUSTER of the slab from L2 and multicasts it to every CTA of the cluster
+            constexpr uint32_t PART = B_SLOT / CLUSTER;
+            bulk_load_mc(b0 + sb * B_SLOT + crank * PART, src + (int64_t)j * (B_SLOT / 4) + crank * (PART / 4), PART,
+                         bar(B_FULL + sb), (uint16_t)((1u << CLUSTER) - 1u));
           }
         }
       }
@@ -517,7 +670,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1) mlp_tc_kernel(const tc::Params
   }
 
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();   // no CTA leaves while a peer may still multicast into its shared memory / barriers
   if (warp == WARP_MMA) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
@@ -544,18 +697,26 @@ __global__ void pack_tc_kernel(const float* __restrict__ wt /*[K_src][256]*/, co
   base[tc::B_HALF / 4 + off] = lo;
 }
 
-// TC first-layer column k -> FFMA first-layer column (both in "our" orders; see FieldLayout)
+// TC first-layer column k -> FFMA first-layer column (both in "our" orders; see FieldLayout).
+// Builder half h (0/1) owns features F(g, h, i) = 8 g + 4 h + i (g < 4, i < 4) and columns [8h, 8h+8) of each slab:
+//   raw slab s (2):       col 8h + 4u + i  = feature F(2s + u, h, i)            (u < 2)
+//   band slab (b, g):     col 8h + i       = sin(2^b F(g, h, i)),  col 8h + 4 + i = cos(2^b F(g, h, i))
 static std::vector<int32_t> tc_first_layer_map(const FieldLayout& L, bool color) {
   const int off = color ? L.off_ft : L.off_fg;
   const int Lf = color ? L.Lft : L.Lfg;
   std::vector<int32_t> m;
   for (int k = 0; k < off; ++k) m.push_back(k);                 // head block: identical order
-  for (int f = 0; f < FEAT; ++f) m.push_back(off + f);          // raw features
+  auto F = [](int g, int h, int i) { return 8 * g + 4 * h + i; };
+  for (int s = 0; s < 2; ++s)
+    for (int h = 0; h < 2; ++h)
+      for (int u = 0; u < 2; ++u)
+        for (int i = 0; i < 4; ++i) m.push_back(off + F(2 * s + u, h, i));
   for (int b = 0; b < Lf; ++b)
-    for (int h = 0; h < 4; ++h) {
-      for (int i = 0; i < 8; ++i) m.push_back(off + (1 + 2 * b) * FEAT + h * 8 + i);  // sin block
-      for (int i = 0; i < 8; ++i) m.push_back(off + (2 + 2 * b) * FEAT + h * 8 + i);  // cos block
-    }
+    for (int g = 0; g < 4; ++g)
+      for (int h = 0; h < 2; ++h) {
+        for (int i = 0; i < 4; ++i) m.push_back(off + (1 + 2 * b) * FEAT + F(g, h, i));  // sin block
+        for (int i = 0; i < 4; ++i) m.push_back(off + (2 + 2 * b) * FEAT + F(g, h, i));  // cos block
+      }
   return m;
 }
 
@@ -619,6 +780,14 @@ static int launch_tc(const nmb_field* f, const MlpFfma& fm, const MlpTc& tm, con
   prm.P = P;
   prm.out0 = out0;
   prm.out1 = out1;
+  prm.dbg = nullptr;
+  static const bool want_prof = getenv("NMB_TC_PROFILE") != nullptr;
+  static unsigned long long* dbg_dev = nullptr;
+  if (want_prof) {
+    if (!dbg_dev) NMB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&dbg_dev), 8 * sizeof(unsigned long long)));
+    NMB_CUDA_OK(cudaMemsetAsync(dbg_dev, 0, 8 * sizeof(unsigned long long), stream));
+    prm.dbg = dbg_dev;
+  }
   constexpr int PTS = (MODE == 1) ? 64 : 128;
   const size_t smem = tc::SmemLayout::total;
   static bool attr_set = false;
@@ -627,10 +796,24 @@ static int launch_tc(const nmb_field* f, const MlpFfma& fm, const MlpTc& tm, con
     attr_set = true;
   }
   const int64_t tiles = ceil_div(P, PTS);
-  const int64_t grid = tiles < (int64_t)sm_count() ? tiles : (int64_t)sm_count();
+  int64_t grid = tiles < (int64_t)sm_count() ? tiles : (int64_t)sm_count();
+  grid = align_up(grid, tc::CLUSTER);
+  if (grid > sm_count()) grid -= tc::CLUSTER;
+  if (grid < tc::CLUSTER) grid = tc::CLUSTER;
   ProfScope prof(MODE == 2 ? PROF_COLOR : (MODE == 1 ? PROF_GEO_JVP : PROF_GEO), P, stream);
   mlp_tc_kernel<MODE><<<(unsigned)grid, tc::THREADS, smem, stream>>>(prm);
   NMB_LAUNCH_OK();
+  if (want_prof) {
+    unsigned long long h[8];
+    NMB_CUDA_OK(cudaMemcpyAsync(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    NMB_CUDA_OK(cudaStreamSynchronize(stream));
+    const double ne = 8.0 * grid, nm = 1.0 * grid;  // 8 epilogue warps and 1 MMA thread per CTA report
+    fprintf(stderr,
+            "[tc-prof] mode %d P %lld grid %lld | epilogue warp avg cycles: total %.0f wait D_FULL %.0f wait A_EMPTY %.0f | "
+            "MMA thread: total %.0f wait D_EMPTY %.0f wait A_FULL(L0) %.0f wait A_FULL(hidden) %.0f wait B_FULL %.0f\n",
+            MODE, (long long)P, (long long)grid, h[2] / ne, h[0] / ne, h[1] / ne, h[7] / nm, h[3] / nm, h[4] / nm,
+            h[5] / nm, h[6] / nm);
+  }
   return 0;
 }
 

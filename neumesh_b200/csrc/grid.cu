@@ -394,6 +394,16 @@ __device__ __forceinline__ float box_dist_rn(float qx, float qy, float qz, const
 // distance while the box bound is short by up to the box size; the number of nodes that survive pruning drops from
 // ~2*pi*D/size per level to a handful.  The disc value is deflated a little so that fp32 rounding can never make it
 // exceed a true distance (r and t are inflated at build time as well).
+__device__ __forceinline__ float disc_bound(float qx, float qy, float qz, const float4& cr, const float4& ut) {
+  const float dx = qx - cr.x, dy = qy - cr.y, dz = qz - cr.z;
+  const float a = ut.x * dx + ut.y * dy + ut.z * dz;
+  const float dd = dx * dx + dy * dy + dz * dz;
+  const float b = sqrtf(fmaxf(dd - a * a, 0.f));
+  const float h = fmaxf(fabsf(a) - ut.w, 0.f);
+  const float l = fmaxf(b - cr.w, 0.f);
+  return (h * h + l * l) * 0.99998f - 1e-12f;
+}
+
 __device__ __forceinline__ float node_bound(float qx, float qy, float qz, const float4& lo, const float4& hi,
                                             const float4& cr, const float4& ut) {
   const float bd = box_dist_rn(qx, qy, qz, lo, hi);
@@ -407,20 +417,26 @@ __device__ __forceinline__ float node_bound(float qx, float qy, float qz, const 
   return fmaxf(bd, disc);
 }
 
-// Insert (nd, ni) into the ascending list d[0..K-1] (precondition nd < d[K-1]); branch-free, strict '<' keeps
-// the earlier candidate on exact ties.
+// Candidates are ranked by the total order (squared distance, slot index): the K smallest under it are unique, so
+// the result does not depend on the order in which the walk meets the points (cold walk, warm-started walk and
+// brute force agree bit for bit even when distances tie exactly).
+__device__ __forceinline__ bool cand_less(float da, int32_t ia, float db, int32_t ib) {
+  return da < db || (da == db && ia < ib);
+}
+
+// Insert (nd, ni) into the ascending list d[0..K-1] (precondition: (nd, ni) ranks before slot K-1); branch-free.
 template <int K>
 __device__ __forceinline__ void topk_insert(float (&d)[K], int32_t (&ix)[K], float nd, int32_t ni) {
 #pragma unroll
   for (int k = K - 1; k > 0; --k) {
-    const bool from_above = nd < d[k - 1];  // old d[k-1] (slots above k are still untouched)
-    const bool here = nd < d[k];            // old d[k]
+    const bool from_above = cand_less(nd, ni, d[k - 1], ix[k - 1]);  // old slot k-1 (still untouched)
+    const bool here = cand_less(nd, ni, d[k], ix[k]);                // old slot k
     const float dk = from_above ? d[k - 1] : (here ? nd : d[k]);
     const int32_t ik = from_above ? ix[k - 1] : (here ? ni : ix[k]);
     d[k] = dk;
     ix[k] = ik;
   }
-  if (nd < d[0]) {
+  if (cand_less(nd, ni, d[0], ix[0])) {
     d[0] = nd;
     ix[0] = ni;
   }
@@ -428,7 +444,7 @@ __device__ __forceinline__ void topk_insert(float (&d)[K], int32_t (&ix)[K], flo
 
 #define NMB_CSWAP(a, b)                                   \
   {                                                       \
-    const bool s_ = cd[a] < cd[b];                        \
+    const bool s_ = cand_less(cd[a], cn[a], cd[b], cn[b]); \
     const float t_ = s_ ? cd[a] : cd[b];                  \
     const int32_t u_ = s_ ? cn[a] : cn[b];                \
     cd[a] = s_ ? cd[b] : cd[a];                           \
@@ -436,69 +452,129 @@ __device__ __forceinline__ void topk_insert(float (&d)[K], int32_t (&ix)[K], flo
     cd[b] = t_;                                           \
     cn[b] = u_;                                           \
   }
+// 19-comparator sorting network on (cd[8], cn[8]), DESCENDING (largest first)
+#define NMB_SORT8_DESC()                                                      \
+  NMB_CSWAP(0, 1) NMB_CSWAP(2, 3) NMB_CSWAP(4, 5) NMB_CSWAP(6, 7)              \
+  NMB_CSWAP(0, 2) NMB_CSWAP(1, 3) NMB_CSWAP(4, 6) NMB_CSWAP(5, 7)              \
+  NMB_CSWAP(1, 2) NMB_CSWAP(5, 6) NMB_CSWAP(0, 4) NMB_CSWAP(3, 7)              \
+  NMB_CSWAP(1, 5) NMB_CSWAP(2, 6)                                              \
+  NMB_CSWAP(1, 4) NMB_CSWAP(3, 6)                                              \
+  NMB_CSWAP(2, 4) NMB_CSWAP(3, 5)                                              \
+  NMB_CSWAP(3, 4)
 
 // Depth-first, nearest-child-first walk.  On return d[]/ix[] hold the K nearest points (ascending squared
 // distance; ix = slot in the Morton-sorted point array).
-template <int K>
+//   WARM = false: d[] / ix[] are initialised here (empty list).
+//   WARM = true : the caller pre-loaded d[] / ix[] with K DISTINCT real points and their distances to q, sorted
+//                 ascending (e.g. the neighbours of the previous sample on the same ray).  The walk then starts with
+//                 a tight pruning bound; a point already in the list is never inserted twice.
+template <int K, bool WARM>
 __device__ __forceinline__ void knn_walk(const float4* __restrict__ nodes, const float4* __restrict__ pts, float qx,
                                          float qy, float qz, float (&d)[K], int32_t (&ix)[K]) {
+  if (!WARM) {
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    d[k] = CUDART_INF_F;
-    ix[k] = 0;
+    for (int k = 0; k < K; ++k) {
+      d[k] = CUDART_INF_F;
+      ix[k] = 0x7fffffff;
+    }
   }
   int32_t sn[STACK_MAX];
   float sd[STACK_MAX];
-  int sp = 0;
+  int sp = 1;
   sn[0] = 0;
   sd[0] = 0.f;
-  sp = 1;
-  while (sp > 0) {
-    --sp;
-    const int32_t n = sn[sp];
-    if (sd[sp] >= d[K - 1]) continue;
-    const float4 a = __ldg(&nodes[NODE_F4 * n]);
-    const float4 b = __ldg(&nodes[NODE_F4 * n + 1]);
-    const int32_t link = __float_as_int(a.w);
-    const int32_t cnt = __float_as_int(b.w);
-    if (cnt < 0) {
-      const int32_t e = link - cnt;
-      for (int32_t i = link; i < e; ++i) {
-        const float4 p = __ldg(&pts[i]);
-        const float dd = sq_dist_rn(qx, qy, qz, p.x, p.y, p.z);
-        if (dd < d[K - 1]) topk_insert<K>(d, ix, dd, i);
+  // "while-while" traversal: every lane first descends through INTERNAL nodes until it holds a leaf, then all lanes
+  // of the warp scan their leaves together - the two code paths are not interleaved lane by lane, which keeps far
+  // more lanes active per issued instruction than a single pop-and-branch loop.
+  while (true) {
+    int32_t leaf_b = 0, leaf_e = 0;
+    while (sp > 0) {
+      --sp;
+      const int32_t n = sn[sp];
+      if (sd[sp] > d[K - 1]) continue;   // '>' (not '>='): an equidistant point with a smaller index may still enter
+      const float4 a = __ldg(&nodes[NODE_F4 * n]);
+      const float4 b = __ldg(&nodes[NODE_F4 * n + 1]);
+      const int32_t link = __float_as_int(a.w);
+      const int32_t cnt = __float_as_int(b.w);
+      if (cnt < 0) {
+        leaf_b = link;
+        leaf_e = link - cnt;
+        break;
       }
-    } else {
       float cd[8];
       int32_t cn[8];
       const float worst = d[K - 1];
+      int m = 0, only = 0;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         cd[c] = CUDART_INF_F;
         cn[c] = link + c;
         if (c < cnt) {
           const float4* nc = nodes + NODE_F4 * (link + c);
-          const float bd = node_bound(qx, qy, qz, __ldg(nc), __ldg(nc + 1), __ldg(nc + 2), __ldg(nc + 3));
-          cd[c] = bd < worst ? bd : CUDART_INF_F;
+          // box first (cheap, exact-safe); the disc bound is only evaluated for children the box cannot reject
+          float bd = box_dist_rn(qx, qy, qz, __ldg(nc), __ldg(nc + 1));
+          if (bd <= worst) {
+            bd = fmaxf(bd, disc_bound(qx, qy, qz, __ldg(nc + 2), __ldg(nc + 3)));
+            if (bd <= worst) {
+              cd[c] = bd;
+              ++m;
+              only = c;
+            }
+          }
         }
       }
-      // 19-comparator sorting network, DESCENDING (largest first) so that the nearest child is pushed last
-      NMB_CSWAP(0, 1) NMB_CSWAP(2, 3) NMB_CSWAP(4, 5) NMB_CSWAP(6, 7)
-      NMB_CSWAP(0, 2) NMB_CSWAP(1, 3) NMB_CSWAP(4, 6) NMB_CSWAP(5, 7)
-      NMB_CSWAP(1, 2) NMB_CSWAP(5, 6) NMB_CSWAP(0, 4) NMB_CSWAP(3, 7)
-      NMB_CSWAP(1, 5) NMB_CSWAP(2, 6)
-      NMB_CSWAP(1, 4) NMB_CSWAP(3, 6)
-      NMB_CSWAP(2, 4) NMB_CSWAP(3, 5)
-      NMB_CSWAP(3, 4)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        if (cd[c] < CUDART_INF_F && sp < STACK_MAX) {
-          sn[sp] = cn[c];
-          sd[sp] = cd[c];
+      if (m == 1) {
+        if (sp < STACK_MAX) {
+          sn[sp] = link + only;
+          sd[sp] = cd[only];
           ++sp;
+        }
+      } else if (m > 1) {
+        NMB_SORT8_DESC()   // nearest child ends up pushed last
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (cd[c] < CUDART_INF_F && sp < STACK_MAX) {
+            sn[sp] = cn[c];
+            sd[sp] = cd[c];
+            ++sp;
+          }
         }
       }
     }
+    if (leaf_e == leaf_b) break;   // stack exhausted without another leaf
+    for (int32_t i = leaf_b; i < leaf_e; ++i) {
+      const float4 p = __ldg(&pts[i]);
+      const float dd = sq_dist_rn(qx, qy, qz, p.x, p.y, p.z);
+      if (cand_less(dd, i, d[K - 1], ix[K - 1])) {
+        bool dup = false;
+        if (WARM) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) dup |= (ix[k] == i);
+        }
+        if (!dup) topk_insert<K>(d, ix, dd, i);
+      }
+    }
+  }
+}
+
+// re-rank K known points against a new query: distances recomputed, then sorted ascending (same network, reversed)
+template <int K>
+__device__ __forceinline__ void warm_rerank(const float4* __restrict__ pts, float qx, float qy, float qz,
+                                            float (&d)[K], int32_t (&ix)[K]) {
+  static_assert(K == 8, "sorting network is for 8 entries");
+  float cd[8];
+  int32_t cn[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 p = __ldg(&pts[ix[k]]);
+    cd[k] = sq_dist_rn(qx, qy, qz, p.x, p.y, p.z);
+    cn[k] = ix[k];
+  }
+  NMB_SORT8_DESC()
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    d[k] = cd[7 - k];
+    ix[k] = cn[7 - k];
   }
 }
 #undef NMB_CSWAP
@@ -563,7 +639,7 @@ knn_distance_kernel(const float4* __restrict__ nodes, const float4* __restrict__
   load_query(src, p, qx, qy, qz);
   float d2[KNN_K];
   int32_t ix[KNN_K];
-  knn_walk<KNN_K>(nodes, pts, qx, qy, qz, d2, ix);
+  knn_walk<KNN_K, false>(nodes, pts, qx, qy, qz, d2, ix);
   float w[KNN_K], ds, grad[3];
   mesh_distance_point(pts, indicator, w1, qx, qy, qz, d2, ix, w, ds, grad);
   out.ds[p] = ds;
@@ -579,10 +655,58 @@ knn_distance_kernel(const float4* __restrict__ nodes, const float4* __restrict__
   }
 }
 
+// Ray-ordered variant: one thread per RAY walks its S samples in depth order and warm-starts every query with the
+// previous sample's neighbours (consecutive samples are <~0.03 apart, so the initial 8th-best bound is already within
+// a few percent of the final one and the octree walk prunes almost everything).  A warp = 32 neighbouring rays.
+__global__ void __launch_bounds__(128)
+knn_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts, const float4* __restrict__ indicator,
+                float w1, PointSrc src, int S, KnnOut out) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= src.R) return;
+  const float ox = src.rays_o[r * 3 + 0], oy = src.rays_o[r * 3 + 1], oz = src.rays_o[r * 3 + 2];
+  const float dx = src.rays_d[r * 3 + 0], dy = src.rays_d[r * 3 + 1], dz = src.rays_d[r * 3 + 2];
+  float d2[KNN_K];
+  int32_t ix[KNN_K];
+  for (int s = 0; s < S; ++s) {
+    const int64_t p = (int64_t)s * src.R + r;
+    const float z = src.z[p];
+    const float qx = __fadd_rn(ox, __fmul_rn(z, dx));
+    const float qy = __fadd_rn(oy, __fmul_rn(z, dy));
+    const float qz = __fadd_rn(oz, __fmul_rn(z, dz));
+    if (s == 0) {
+      knn_walk<KNN_K, false>(nodes, pts, qx, qy, qz, d2, ix);
+    } else {
+      warm_rerank<KNN_K>(pts, qx, qy, qz, d2, ix);
+      knn_walk<KNN_K, true>(nodes, pts, qx, qy, qz, d2, ix);
+    }
+    float w[KNN_K], ds, grad[3];
+    mesh_distance_point(pts, indicator, w1, qx, qy, qz, d2, ix, w, ds, grad);
+    out.ds[p] = ds;
+#pragma unroll
+    for (int k = 0; k < KNN_K; ++k) {
+      out.slot[k * out.stride + p] = ix[k];
+      out.w[k * out.stride + p] = w[k];
+    }
+    if (out.grad) {
+      out.grad[0 * out.stride + p] = grad[0];
+      out.grad[1 * out.stride + p] = grad[1];
+      out.grad[2 * out.stride + p] = grad[2];
+    }
+  }
+}
+
+constexpr int64_t RAY_KERNEL_MIN_RAYS = 32768;  // below this the per-point kernels expose more parallelism
+
 int launch_knn_distance(const nmb_grid* g, const float4* indicator_sorted, float w1, PointSrc src, int64_t P,
                         KnnOut out, cudaStream_t stream) {
   if (P <= 0) return 0;
   ProfScope prof(PROF_KNN, P, stream);
+  if (!src.xyz && src.R >= RAY_KERNEL_MIN_RAYS && P % src.R == 0) {
+    knn_rays_kernel<<<(unsigned)ceil_div(src.R, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src,
+                                                                       (int)(P / src.R), out);
+    NMB_LAUNCH_OK();
+    return 0;
+  }
   knn_distance_kernel<<<(unsigned)ceil_div(P, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src,
                                                                       P, out);
   NMB_LAUNCH_OK();
@@ -608,12 +732,66 @@ bound_scan_kernel(const float4* __restrict__ nodes, const float4* __restrict__ p
   const float qz = __fadd_rn(rays_o[r * 3 + 2], __fmul_rn(d, dirs[r * 3 + 2]));
   float d2[KNN_K];
   int32_t ix[KNN_K];
-  knn_walk<KNN_K>(nodes, pts, qx, qy, qz, d2, ix);
+  knn_walk<KNN_K, false>(nodes, pts, qx, qy, qz, d2, ix);
   float w[KNN_K], ds, grad[3];
   mesh_distance_point(pts, indicator, w1, qx, qy, qz, d2, ix, w, ds, grad);
   if (ds < thresh) {
     atomicMin(&bnear[r], __float_as_int(d));
     atomicMax(&bfar[r], __float_as_int(d));
+  }
+}
+
+// Ray-ordered bounded-near/far scan.  near = min, far = max over the samples with ds < thresh, and the depths are
+// monotone in the sample index, so near is the FIRST hit scanning from the front and far the first hit scanning from
+// the back: samples between the two can change neither and are not evaluated.  Output-identical to the full scan.
+__global__ void __launch_bounds__(128)
+bound_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts,
+                  const float4* __restrict__ indicator, float w1, const float* __restrict__ rays_o,
+                  const float* __restrict__ dirs, const float* __restrict__ near, const float* __restrict__ far,
+                  int64_t R, int n_grid, float thresh, int32_t* __restrict__ bnear, int32_t* __restrict__ bfar) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float ox = rays_o[r * 3 + 0], oy = rays_o[r * 3 + 1], oz = rays_o[r * 3 + 2];
+  const float dx = dirs[r * 3 + 0], dy = dirs[r * 3 + 1], dz = dirs[r * 3 + 2];
+  const float nr = near[r], fr = far[r];
+  float d2[KNN_K];
+  int32_t ix[KNN_K];
+  auto ds_at = [&](int s, bool warm, float& depth) {
+    const float t = linspace01(s, n_grid);
+    depth = __fadd_rn(__fmul_rn(nr, __fsub_rn(1.0f, t)), __fmul_rn(fr, t));  // renderer.py:81
+    const float qx = __fadd_rn(ox, __fmul_rn(depth, dx));
+    const float qy = __fadd_rn(oy, __fmul_rn(depth, dy));
+    const float qz = __fadd_rn(oz, __fmul_rn(depth, dz));
+    if (warm) {
+      warm_rerank<KNN_K>(pts, qx, qy, qz, d2, ix);
+      knn_walk<KNN_K, true>(nodes, pts, qx, qy, qz, d2, ix);
+    } else {
+      knn_walk<KNN_K, false>(nodes, pts, qx, qy, qz, d2, ix);
+    }
+    float w[KNN_K], ds, grad[3];
+    mesh_distance_point(pts, indicator, w1, qx, qy, qz, d2, ix, w, ds, grad);
+    return ds;
+  };
+  int first = -1;
+  float depth = 0.f;
+  for (int s = 0; s < n_grid; ++s) {
+    if (ds_at(s, s > 0, depth) < thresh) {
+      first = s;
+      bnear[r] = __float_as_int(depth);
+      break;
+    }
+  }
+  if (first < 0) return;  // no sample inside the shell: bnear / bfar keep their "unset" values
+  for (int s = n_grid - 1; s >= first; --s) {
+    // s == first is known to be a hit: the loop always terminates with bfar set
+    if (s == first || ds_at(s, s < n_grid - 1, depth) < thresh) {
+      if (s == first) {
+        const float t = linspace01(s, n_grid);
+        depth = __fadd_rn(__fmul_rn(nr, __fsub_rn(1.0f, t)), __fmul_rn(fr, t));
+      }
+      bfar[r] = __float_as_int(depth);
+      break;
+    }
   }
 }
 
@@ -623,6 +801,12 @@ int launch_bound_scan(const nmb_grid* g, const float4* indicator, float w1, cons
   const int64_t n = R * n_grid;
   if (n <= 0) return 0;
   ProfScope prof(PROF_BOUND, n, stream);
+  if (R >= RAY_KERNEL_MIN_RAYS) {
+    bound_rays_kernel<<<(unsigned)ceil_div(R, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator, w1, rays_o, dirs,
+                                                                     near, far, R, n_grid, thresh, bnear, bfar);
+    NMB_LAUNCH_OK();
+    return 0;
+  }
   bound_scan_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator, w1, rays_o, dirs,
                                                                     near, far, R, n_grid, thresh, bnear, bfar);
   NMB_LAUNCH_OK();
