@@ -40,7 +40,8 @@ constexpr int CLUSTER = 2;                 // CTAs per cluster sharing every wei
 // NOTE two separate A rings: an mbarrier parity wait is only meaningful while the waiter is at most one phase
 // ahead of the barrier.  The builder runs a whole tile ahead of the epilogue, so the two producer groups must not
 // share one ring (a shared ring deadlocks as soon as a CTA processes a second tile).
-constexpr int N_EPI = 256;                 // 2 groups x 4 warps: group g drains the 16-column chunks j with j % 2 == g
+constexpr int N_EPI = 512;                 // 16 warps: quadrant = w & 3 (TMEM lanes), group g = (w >> 2) & 1 drains the chunks
+                                           // j with j % 2 == g, half hh = w >> 3 takes columns [8 hh, 8 hh + 8) of a chunk
 constexpr int N_BUILD = 256;               // 2 threads per row: half h builds columns [8h, 8h+8) of every first-layer slab
 constexpr int THREADS = N_EPI + N_BUILD + 64;
 constexpr int WARP_BUILD = N_EPI / 32, WARP_MMA = (N_EPI + N_BUILD) / 32;
@@ -51,8 +52,8 @@ struct SmemLayout {
   static constexpr int a_off = 0;
   static constexpr int b_off = NA * A_SLOT;
   static constexpr int sig_off = b_off + NB * B_SLOT;          // [group][parity] buffers
-  static constexpr int part_off = sig_off + 4 * SIG_BUF * 4;   // last-layer partial sums of group 1: [3][128]
-  static constexpr int const_off = part_off + 3 * ROWS * 4;    // biases + output weights
+  static constexpr int part_off = sig_off + 4 * SIG_BUF * 4;   // last-layer partial sums: [3 helpers][3][128]
+  static constexpr int const_off = part_off + 9 * ROWS * 4;    // biases + output weights
   static constexpr int bar_off = const_off + CONST_FLOATS * 4;
   static constexpr int total = bar_off + 256;
 };
@@ -170,6 +171,18 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;"
                : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
                  "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait8(uint32_t (&r)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
                :
                : "memory");
 }
@@ -309,7 +322,7 @@ mlp_tc_kernel(const tc::Params prm) {
 
   if (tid == 0) {
     for (int i = 0; i < NA; ++i) {
-      mbar_init(bar(A_FULL + i), i < NA0 ? N_BUILD : 128);   // first-layer slabs: both half-row builders arrive
+      mbar_init(bar(A_FULL + i), 256);   // two half-row producers per row (builders for slots < NA0, epilogue otherwise)
       mbar_init(bar(A_EMPTY + i), 1);
     }
     for (int i = 0; i < NB; ++i) {
@@ -340,8 +353,9 @@ mlp_tc_kernel(const tc::Params prm) {
 
   if (warp < WARP_BUILD) {
     // =========================================== epilogue ===========================================
-    const int grp = warp >> 2;                 // 0 / 1: which half of the chunks this warp-group drains
-    const int r = tid & 127;                   // row == TMEM lane (warp % 4 selects the lane quadrant)
+    const int grp = (warp >> 2) & 1;           // which half of the chunks this warp drains
+    const int hh = warp >> 3;                  // which 8 columns of a chunk
+    const int r = (warp & 3) * 32 + (tid & 31);            // row == TMEM lane
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     float* sig_g = sig + grp * 2 * SIG_BUF;
     uint32_t g = 0;                            // global layer counter of this CTA
@@ -360,65 +374,62 @@ mlp_tc_kernel(const tc::Params prm) {
         const uint32_t buf = g & 1u;
         mbar_wait_t(bar(D_FULL + buf), (g >> 1) & 1u, prof, t_dfull);
         tc_fence_after();
-        const float* bl = cst + l * MLP_W;
+        const float* bl = cst + l * MLP_W + 8 * hh;
         const bool last = (l == NL - 1);
         float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-        // software-pipelined TMEM reads: the load of this group's NEXT chunk is in flight while the current one is
+        // software-pipelined TMEM reads: the load of this warp's NEXT chunk is in flight while the current one is
         // being activated / split / stored
-        uint32_t raw[16];
-        tmem_ld16_issue(tmem_base + lane_base + buf * 256u + (uint32_t)(grp * SLAB_K), raw);
+        const uint32_t t_row = tmem_base + lane_base + buf * 256u + (uint32_t)(8 * hh);
+        uint32_t raw[8];
+        tmem_ld8_issue(t_row + (uint32_t)(grp * SLAB_K), raw);
 #pragma unroll 1
         for (int j = grp; j < N_CHUNK; j += 2) {
-          float v[16];
-          tmem_ld_wait(raw);
+          float v[8];
+          tmem_ld_wait8(raw);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[i]);
-          if (j + 2 < N_CHUNK) tmem_ld16_issue(tmem_base + lane_base + buf * 256u + (uint32_t)((j + 2) * SLAB_K), raw);
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[i]);
+          if (j + 2 < N_CHUNK) tmem_ld8_issue(t_row + (uint32_t)((j + 2) * SLAB_K), raw);
           if (MODE == 2) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + bl[j * 16 + i], 0.f);
+            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i] + bl[j * 16 + i], 0.f);
           } else if (MODE == 0) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 0; i < 8; ++i) {
               const float z = v[i] + bl[j * 16 + i];
-              const float a = z * 100.f;
               const float y = __log2f(1.0f + fast_exp2(z * K_EXP)) * K_LOG;
-              v[i] = a > 20.f ? z : y;
+              v[i] = z > 0.2f ? z : y;   // 100 z > 20
             }
           } else {
             // MODE 1: value rows (0..63) publish e = exp(100 z); both halves then work in parallel:
             // value: softplus = log(1 + e) / 100, tangent: sigma'(z) * (W t) with sigma' = e / (1 + e)
             float* sb = sig_g + ((j >> 1) & 1) * SIG_BUF;
-            float e[16];
+            float e[8];
             if (r < 64) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
+              for (int i = 0; i < 8; ++i) {
                 v[i] = v[i] + bl[j * 16 + i];
                 e[i] = fast_exp2(v[i] * K_EXP);
               }
-#pragma unroll
-              for (int c = 0; c < 4; ++c)
-                *reinterpret_cast<float4*>(sb + r * 16 + c * 4) = make_float4(e[c * 4], e[c * 4 + 1], e[c * 4 + 2], e[c * 4 + 3]);
+              *reinterpret_cast<float4*>(sb + r * 16 + 8 * hh) = make_float4(e[0], e[1], e[2], e[3]);
+              *reinterpret_cast<float4*>(sb + r * 16 + 8 * hh + 4) = make_float4(e[4], e[5], e[6], e[7]);
             }
-            if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-            else asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (grp == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+            else asm volatile("bar.sync 2, 256;" ::: "memory");
             if (r < 64) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
+              for (int i = 0; i < 8; ++i) {
                 const float y = __log2f(1.0f + e[i]) * K_LOG;
-                v[i] = (v[i] * 100.f > 20.f) ? v[i] : y;
+                v[i] = (v[i] > 0.2f) ? v[i] : y;
               }
             } else {
+              const float4 e0 = *reinterpret_cast<const float4*>(sb + (r - 64) * 16 + 8 * hh);
+              const float4 e1 = *reinterpret_cast<const float4*>(sb + (r - 64) * 16 + 8 * hh + 4);
+              const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const float4 ev = *reinterpret_cast<const float4*>(sb + (r - 64) * 16 + c * 4);
-                const float ee[4] = {ev.x, ev.y, ev.z, ev.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  // 100 z > 20  <=>  e > exp(20)
-                  const float sg = ee[i] > 485165195.4097903f ? 1.f : __fdividef(ee[i], ee[i] + 1.f);
-                  v[c * 4 + i] *= sg;
-                }
+              for (int i = 0; i < 8; ++i) {
+                // 100 z > 20  <=>  e > exp(20)
+                const float sg = ee[i] > 485165195.4097903f ? 1.f : __fdividef(ee[i], ee[i] + 1.f);
+                v[i] *= sg;
               }
             }
           }
@@ -426,13 +437,13 @@ mlp_tc_kernel(const tc::Params prm) {
             const uint32_t qs = q + (uint32_t)j;
             const uint32_t slot = NA0 + qs % NA1;
             mbar_wait_t(bar(A_EMPTY + slot), ((qs / NA1) & 1u) ^ 1u, prof, t_aempty);
-            store_a_row(a_ring + slot * A_SLOT, r, v);
+            store_a_half(a_ring + slot * A_SLOT, r, hh, v);
             fence_proxy_async();
             mbar_arrive(bar(A_FULL + slot));
           } else {
-            const float* wo = cst + NL * MLP_W + j * 16;
+            const float* wo = cst + NL * MLP_W + j * 16 + 8 * hh;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 0; i < 8; ++i) {
               o0 = fmaf(v[i], wo[i], o0);
               if (MODE == 2) {
                 o1 = fmaf(v[i], wo[MLP_W + i], o1);
@@ -446,20 +457,26 @@ mlp_tc_kernel(const tc::Params prm) {
         if (!last) {
           q += N_CHUNK;
         } else {
-          // combine the two groups' partial dot products (group 1 -> smem -> group 0)
-          if (grp == 1) {
-            part[r] = o0;
+          // combine the four partial dot products of a row (helpers -> smem -> warp-group (grp 0, hh 0))
+          const int helper = grp + 2 * hh;   // 0 = finaliser, 1..3 = helpers
+          if (helper != 0) {
+            float* pp = part + (helper - 1) * 3 * ROWS;
+            pp[r] = o0;
             if (MODE == 2) {
-              part[ROWS + r] = o1;
-              part[2 * ROWS + r] = o2;
+              pp[ROWS + r] = o1;
+              pp[2 * ROWS + r] = o2;
             }
           }
-          asm volatile("bar.sync 3, 256;" ::: "memory");
-          if (grp == 0) {
-            o0 += part[r];
-            if (MODE == 2) {
-              o1 += part[ROWS + r];
-              o2 += part[2 * ROWS + r];
+          asm volatile("bar.sync 3, 512;" ::: "memory");
+          if (helper == 0) {
+#pragma unroll
+            for (int hlp = 0; hlp < 3; ++hlp) {
+              const float* pp = part + hlp * 3 * ROWS;
+              o0 += pp[r];
+              if (MODE == 2) {
+                o1 += pp[ROWS + r];
+                o2 += pp[2 * ROWS + r];
+              }
             }
             if (valid) {
               if (MODE == 2) {
@@ -475,8 +492,8 @@ mlp_tc_kernel(const tc::Params prm) {
               }
             }
           }
-          // group 1 may only overwrite `part` after group 0 has read it
-          asm volatile("bar.sync 4, 256;" ::: "memory");
+          // helpers may only overwrite `part` after the finaliser has read it
+          asm volatile("bar.sync 4, 512;" ::: "memory");
         }
       }
     }
@@ -807,7 +824,7 @@ static int launch_tc(const nmb_field* f, const MlpFfma& fm, const MlpTc& tm, con
     unsigned long long h[8];
     NMB_CUDA_OK(cudaMemcpyAsync(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost, stream));
     NMB_CUDA_OK(cudaStreamSynchronize(stream));
-    const double ne = 8.0 * grid, nm = 1.0 * grid;  // 8 epilogue warps and 1 MMA thread per CTA report
+    const double ne = 16.0 * grid, nm = 1.0 * grid;  // 16 epilogue warps and 1 MMA thread per CTA report
     fprintf(stderr,
             "[tc-prof] mode %d P %lld grid %lld | epilogue warp avg cycles: total %.0f wait D_FULL %.0f wait A_EMPTY %.0f | "
             "MMA thread: total %.0f wait D_EMPTY %.0f wait A_FULL(L0) %.0f wait A_FULL(hidden) %.0f wait B_FULL %.0f\n",
