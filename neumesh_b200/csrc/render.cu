@@ -8,6 +8,7 @@
 // Per chunk:  rays -> sphere near/far -> [256-sample mesh-distance scan -> bounded near/far]
 //             -> 64 coarse samples -> 4 x { slope/alpha/cdf -> 16 inverse-cdf samples -> sdf -> merge }
 //             -> sdf(+nabla) at the 128 samples, sdf+nabla+colour at the 127 mid-points -> composite.
+#include <cub/cub.cuh>
 #include <math_constants.h>
 
 #include "field.cuh"
@@ -19,11 +20,50 @@ constexpr int RT = 128;  // threads per block of the per-ray kernels
 __device__ __forceinline__ float sigmoid_t(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
 // renderer.py:150-153 (normalise directions) + rend_util.py:179-199 (sphere near/far)
-__global__ void ray_setup_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, int64_t R,
-                                 float radius, int normalize, float* __restrict__ dirs, float* __restrict__ near,
+// Spatial sort key of a ray: 30-bit Morton code of its closest point to the origin (the scene centre).  Rays are
+// rendered in key order so that the 32 rays of a warp form a compact patch: their octree walks then share nodes
+// (coalesced loads) and hit / miss rays are not mixed inside a warp.  Outputs are written back in caller order.
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+  v = (v * 0x00010001u) & 0xFF0000FFu;
+  v = (v * 0x00000101u) & 0x0F00F00Fu;
+  v = (v * 0x00000011u) & 0xC30C30C3u;
+  v = (v * 0x00000005u) & 0x49249249u;
+  return v;
+}
+__global__ void ray_key_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d, int64_t N,
+                               float radius, uint32_t* __restrict__ key, int32_t* __restrict__ idx) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const float ox = rays_o[r * 3], oy = rays_o[r * 3 + 1], oz = rays_o[r * 3 + 2];
+  float dx = rays_d[r * 3], dy = rays_d[r * 3 + 1], dz = rays_d[r * 3 + 2];
+  const float n = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
+  dx /= n; dy /= n; dz /= n;
+  const float t = -(ox * dx + oy * dy + oz * dz);
+  const float s = 511.5f / (2.f * radius);
+  const float m[3] = {ox + t * dx, oy + t * dy, oz + t * dz};
+  uint32_t q[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = m[c] * s + 511.5f;
+    v = fminf(fmaxf(v, 0.f), 1023.f);
+    q[c] = (uint32_t)v;
+  }
+  key[r] = (spread10(q[0]) << 2) | (spread10(q[1]) << 1) | spread10(q[2]);
+  idx[r] = (int32_t)r;
+}
+
+__global__ void ray_setup_kernel(const float* __restrict__ rays_o_all, const float* __restrict__ rays_d_all,
+                                 const int32_t* __restrict__ perm, int64_t R, float radius, int normalize,
+                                 float* __restrict__ orig, float* __restrict__ dirs, float* __restrict__ near,
                                  float* __restrict__ far, int32_t* __restrict__ bnear, int32_t* __restrict__ bfar) {
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= R) return;
+  const int64_t src = perm[r];
+  const float* rays_o = rays_o_all + src * 3 - r * 3;   // so that rays_o[r * 3 + c] addresses ray `src`
+  const float* rays_d = rays_d_all + src * 3 - r * 3;
+  orig[r * 3] = rays_o[r * 3];
+  orig[r * 3 + 1] = rays_o[r * 3 + 1];
+  orig[r * 3 + 2] = rays_o[r * 3 + 2];
   float dx = rays_d[r * 3], dy = rays_d[r * 3 + 1], dz = rays_d[r * 3 + 2];
   if (normalize) {
     // F.normalize: v / max(||v||, 1e-12)
@@ -145,20 +185,35 @@ upsample_kernel(int64_t R, int n, int n_new, float inv_s, const float* __restric
 // in place, from the back.  Ties: either order is equivalent (tied depths carry bit-identical sdf values).
 __global__ void __launch_bounds__(RT)
 merge_kernel(int64_t R, int n, int n_new, float* __restrict__ z, float* __restrict__ sdf,
-             const float* __restrict__ znew, const float* __restrict__ sdfnew) {
+             const float* __restrict__ znew, const float* __restrict__ sdfnew, float* __restrict__ nab,
+             const float* __restrict__ nabnew, int64_t nstride) {
+  // nab / nabnew (nullable): [3][nstride] SoA payload (nabla at the samples) carried through the merge
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= R) return;
   int a = n - 1, b = n_new - 1;
   float za = z[(int64_t)a * R + r], zb = znew[(int64_t)b * R + r];
   for (int o = n + n_new - 1; o >= 0 && b >= 0; --o) {
+    const int64_t dst = (int64_t)o * R + r;
     if (a >= 0 && za > zb) {
-      z[(int64_t)o * R + r] = za;
-      sdf[(int64_t)o * R + r] = sdf[(int64_t)a * R + r];
+      const int64_t src = (int64_t)a * R + r;
+      z[dst] = za;
+      sdf[dst] = sdf[src];
+      if (nab) {
+        nab[dst] = nab[src];
+        nab[nstride + dst] = nab[nstride + src];
+        nab[2 * nstride + dst] = nab[2 * nstride + src];
+      }
       --a;
       if (a >= 0) za = z[(int64_t)a * R + r];
     } else {
-      z[(int64_t)o * R + r] = zb;
-      sdf[(int64_t)o * R + r] = sdfnew[(int64_t)b * R + r];
+      const int64_t src = (int64_t)b * R + r;
+      z[dst] = zb;
+      sdf[dst] = sdfnew[src];
+      if (nab) {
+        nab[dst] = nabnew[src];
+        nab[nstride + dst] = nabnew[nstride + src];
+        nab[2 * nstride + dst] = nabnew[2 * nstride + src];
+      }
       --b;
       if (b >= 0) zb = znew[(int64_t)b * R + r];
     }
@@ -177,10 +232,11 @@ __global__ void __launch_bounds__(RT)
 composite_kernel(int64_t R, int P, float s, int white_bkgd, const float* __restrict__ sdf, const float* __restrict__ zmid,
                  const float* __restrict__ rgb_s /*[3][(P-1)*R]*/, int64_t cstride,
                  const float* __restrict__ nabla_s /*[3][P*R] or null*/, int64_t nstride, float* __restrict__ wbuf,
-                 float* __restrict__ rgb_out, float* __restrict__ depth_out, float* __restrict__ acc_out,
-                 float* __restrict__ normals_out) {
+                 const int32_t* __restrict__ perm, float* __restrict__ rgb_out, float* __restrict__ depth_out,
+                 float* __restrict__ acc_out, float* __restrict__ normals_out) {
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= R) return;
+  const int64_t dst = perm[r];   // caller's ray index
   float c0 = sigmoid_t(__fmul_rn(sdf[r], s));
   float T = 1.0f, acc = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
   for (int j = 0; j + 1 < P; ++j) {
@@ -215,36 +271,36 @@ composite_kernel(int64_t R, int P, float s, int white_bkgd, const float* __restr
     cg = __fadd_rn(cg, bg);
     cb = __fadd_rn(cb, bg);
   }
-  rgb_out[r * 3] = cr;
-  rgb_out[r * 3 + 1] = cg;
-  rgb_out[r * 3 + 2] = cb;
-  depth_out[r] = depth;
-  acc_out[r] = acc;
+  rgb_out[dst * 3] = cr;
+  rgb_out[dst * 3 + 1] = cg;
+  rgb_out[dst * 3 + 2] = cb;
+  depth_out[dst] = depth;
+  acc_out[dst] = acc;
   if (normals_out) {
-    normals_out[r * 3] = nx;
-    normals_out[r * 3 + 1] = ny;
-    normals_out[r * 3 + 2] = nz;
+    normals_out[dst * 3] = nx;
+    normals_out[dst * 3 + 1] = ny;
+    normals_out[dst * 3 + 2] = nz;
   }
 }
 
 // [S][R] sample-major -> [R,S] row-major (detail outputs); C channels with source stride cstride: out [R,S,C]
 __global__ void export_samples_kernel(int64_t R, int S, int C, const float* __restrict__ src, int64_t cstride,
-                                      float* __restrict__ dst) {
+                                      const int32_t* __restrict__ perm, float* __restrict__ dst) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= R * S * C) return;
   const int c = (int)(i % C);
   const int64_t t = i / C;
   const int s = (int)(t % S);
   const int64_t r = t / S;
-  dst[i] = src[c * cstride + (int64_t)s * R + r];
+  dst[((int64_t)perm[r] * S + s) * C + c] = src[c * cstride + (int64_t)s * R + r];
 }
 
 __global__ void export_near_far_kernel(int64_t R, const float* __restrict__ near, const float* __restrict__ far,
-                                       float* __restrict__ dst) {
+                                       const int32_t* __restrict__ perm, float* __restrict__ dst) {
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= R) return;
-  dst[r * 2] = near[r];
-  dst[r * 2 + 1] = far[r];
+  dst[(int64_t)perm[r] * 2] = near[r];
+  dst[(int64_t)perm[r] * 2 + 1] = far[r];
 }
 
 // utils/rend_util.py:97-176: pixel (x, y) -> K^-1 -> normalise -> rotate
@@ -274,7 +330,7 @@ namespace {
 
 struct Workspace {
   // all sizes in floats
-  float *dirs, *near, *far;
+  float *orig, *dirs, *near, *far;
   int32_t *bnear, *bfar;
   float *z, *sdf, *znew, *sdfnew, *wbuf, *zmid;
   float *k_ds, *k_w, *k_grad;
@@ -293,6 +349,7 @@ Workspace carve(void* base, int64_t R, int P, int n_new) {
     return q;
   };
   const int64_t PR = (int64_t)P * R;
+  w.orig = take(3 * R);
   w.dirs = take(3 * R);
   w.near = take(R);
   w.far = take(R);
@@ -339,19 +396,37 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
   NMB_CHECK(!cfg->calc_normal || normals, "calc_normal needs a normals output");
   NMB_CHECK(workspace_bytes >= nmb_render_workspace_bytes(cfg, rays_per_chunk), "workspace too small");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (N <= 0) return 0;
   const int n_iters = cfg->N_upsample_iters;
   const int n_new = n_iters > 0 ? cfg->N_importance / n_iters : 0;
   const int P = cfg->N_samples + n_new * n_iters;
   void* ws_aligned = reinterpret_cast<void*>(align_up(reinterpret_cast<int64_t>(workspace), 256));
   const nmb_grid* g = f->grid;
 
+  // ---- render order: rays sorted by the Morton key of their closest point to the scene centre ----
+  uint32_t *key_in = nullptr, *key_out = nullptr;
+  int32_t *idx_in = nullptr, *perm_all = nullptr;
+  void* sort_tmp = nullptr;
+  size_t sort_bytes = 0;
+  NMB_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, key_in, key_out, idx_in, perm_all, (int)N, 0, 30, stream));
+  NMB_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&key_in), sizeof(uint32_t) * N, stream));
+  NMB_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&key_out), sizeof(uint32_t) * N, stream));
+  NMB_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&idx_in), sizeof(int32_t) * N, stream));
+  NMB_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&perm_all), sizeof(int32_t) * N, stream));
+  NMB_CUDA_OK(cudaMallocAsync(&sort_tmp, sort_bytes, stream));
+  ray_key_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(rays_o, rays_d, N, cfg->obj_bounding_radius, key_in, idx_in);
+  NMB_LAUNCH_OK();
+  NMB_CUDA_OK(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, key_in, key_out, idx_in, perm_all, (int)N, 0, 30, stream));
+  count_launch(3);
+
   for (int64_t c0 = 0; c0 < N; c0 += rays_per_chunk) {
     const int64_t R = (N - c0 < rays_per_chunk) ? (N - c0) : rays_per_chunk;
     Workspace w = carve(ws_aligned, R, P, n_new > 0 ? n_new : 1);
-    const float* ro = rays_o + c0 * 3;
+    const int32_t* perm = perm_all + c0;   // chunk-local ray r  <->  caller's ray perm[r]
+    const float* ro = w.orig;
     const unsigned rb = (unsigned)ceil_div(R, RT);
-    ray_setup_kernel<<<rb, RT, 0, stream>>>(ro, rays_d + c0 * 3, R, cfg->obj_bounding_radius, cfg->normalize_dirs,
-                                            w.dirs, w.near, w.far, w.bnear, w.bfar);
+    ray_setup_kernel<<<rb, RT, 0, stream>>>(rays_o, rays_d, perm, R, cfg->obj_bounding_radius, cfg->normalize_dirs,
+                                            w.orig, w.dirs, w.near, w.far, w.bnear, w.bfar);
     NMB_LAUNCH_OK();
     if (cfg->bounded_near_far) {
       int rc = launch_bound_scan(g, f->indicator.p, f->w1, ro, w.dirs, w.near, w.far, R, 256, 0.1f, w.bnear, w.bfar,
@@ -394,22 +469,23 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
       return 0;
     };
 
-    int rc = eval(w.z, n, w.sdf, nullptr, false);
+    // The reference evaluates the P final samples a second time (renderer.py:271-274: forward_with_nablas when
+    // calc_normal, forward_density_only otherwise).  They are the very points of the coarse / up-sampling passes, so
+    // their sdf is already known (same point, same kernel => same bits) and, with calc_normal, the nabla is obtained
+    // in those passes too (tangent rows) and carried through the merges: no second KNN walk, no second MLP pass.
+    const int64_t PR = (int64_t)P * R;
+    float* nab_pts = cfg->calc_normal ? w.nabla_pts : nullptr;
+    float* nab_new = cfg->calc_normal ? w.nabla_mid : nullptr;   // free until the mid-point pass
+    int rc = eval(w.z, n, w.sdf, nab_pts, false);
     if (rc) return rc;
     for (int it = 0; it < n_iters; ++it) {
       upsample_kernel<<<rb, RT, 0, stream>>>(R, n, n_new, 256.0f * (float)(1 << it), w.z, w.sdf, w.wbuf, w.znew);
       NMB_LAUNCH_OK();
-      rc = eval(w.znew, n_new, w.sdfnew, nullptr, false);
+      rc = eval(w.znew, n_new, w.sdfnew, nab_new, false);
       if (rc) return rc;
-      merge_kernel<<<rb, RT, 0, stream>>>(R, n, n_new, w.z, w.sdf, w.znew, w.sdfnew);
+      merge_kernel<<<rb, RT, 0, stream>>>(R, n, n_new, w.z, w.sdf, w.znew, w.sdfnew, nab_pts, nab_new, PR);
       NMB_LAUNCH_OK();
       n += n_new;
-    }
-    // final samples: sdf at the P points is already known (same points, same kernel => same bits);
-    // calc_normal re-evaluates them with tangents (renderer.py:271-274)
-    if (cfg->calc_normal) {
-      rc = eval(w.z, P, w.sdf, w.nabla_pts, false);
-      if (rc) return rc;
     }
     midpoints_kernel<<<(unsigned)ceil_div(R * (P - 1), 256), 256, 0, stream>>>(R, P, w.z, w.zmid);
     NMB_LAUNCH_OK();
@@ -417,14 +493,13 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
     rc = eval(w.zmid, P - 1, w.sdf_mid, need_mid_nabla ? w.nabla_mid : nullptr, true);
     if (rc) return rc;
     composite_kernel<<<rb, RT, 0, stream>>>(R, P, f->s, cfg->white_bkgd, w.sdf, w.zmid, w.rgb, (int64_t)P * R,
-                                            cfg->calc_normal ? w.nabla_pts : nullptr, (int64_t)P * R, w.wbuf,
-                                            rgb + c0 * 3, depth + c0, acc + c0, normals ? normals + c0 * 3 : nullptr);
+                                            cfg->calc_normal ? w.nabla_pts : nullptr, (int64_t)P * R, w.wbuf, perm,
+                                            rgb, depth, acc, normals);
     NMB_LAUNCH_OK();
     if (detail) {
       auto ex = [&](float* dst, const float* src, int S, int C, int64_t cstride) -> int {
         if (!dst) return 0;
-        export_samples_kernel<<<(unsigned)ceil_div(R * S * C, 256), 256, 0, stream>>>(R, S, C, src, cstride,
-                                                                                    dst + c0 * S * C);
+        export_samples_kernel<<<(unsigned)ceil_div(R * S * C, 256), 256, 0, stream>>>(R, S, C, src, cstride, perm, dst);
         NMB_LAUNCH_OK();
         return 0;
       };
@@ -434,11 +509,16 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
       if ((rc = ex(detail->radiance, w.rgb, P - 1, 3, (int64_t)P * R))) return rc;
       if ((rc = ex(detail->sdf_mid, w.sdf_mid, P - 1, 1, 0))) return rc;
       if (detail->near_far) {
-        export_near_far_kernel<<<rb, RT, 0, stream>>>(R, w.near, w.far, detail->near_far + c0 * 2);
+        export_near_far_kernel<<<rb, RT, 0, stream>>>(R, w.near, w.far, perm, detail->near_far);
         NMB_LAUNCH_OK();
       }
     }
   }
+  NMB_CUDA_OK(cudaFreeAsync(key_in, stream));
+  NMB_CUDA_OK(cudaFreeAsync(key_out, stream));
+  NMB_CUDA_OK(cudaFreeAsync(idx_in, stream));
+  NMB_CUDA_OK(cudaFreeAsync(perm_all, stream));
+  NMB_CUDA_OK(cudaFreeAsync(sort_tmp, stream));
   return 0;
 }
 

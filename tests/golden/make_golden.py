@@ -72,6 +72,35 @@ def make_case(name, level, H, W, cfg, render_kwargs, seed):
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def make_train_case(name, level, n_rays, seed):
+    """Gradients of a training-style loss through the UNMODIFIED reference renderer + model (config 4 semantics:
+    grad enabled, calc_normal, eikonal double backward; perturb=False so that the sample positions are deterministic)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    ns = ref_harness.load()
+    cfg = synth.ModelConfig()
+    mesh = synth.icosphere_mesh(level, seed=seed)
+    sd = synth.make_state_dict(mesh, cfg, seed=seed + 1)
+    model = ref_harness.build_reference_model(mesh, cfg, sd)
+    model.train()
+    o, d = synth.frame_rays(24, 24, view=2)
+    sel = torch.linspace(0, o.shape[0] - 1, n_rays).long()
+    o, d = o[sel].contiguous(), d[sel].contiguous()
+    rgb, depth, ex = ns.renderer.volume_render(o, d, model, rayschunk=4096, **helpers.TRAIN_KW)
+    loss = helpers.train_loss(rgb, depth, ex)
+    loss.backward()
+    params = dict(model.named_parameters())
+    out = dict(level=np.int64(level), seed=np.int64(seed), state_digest=np.array(state_digest(sd)),
+               rays_o=o.numpy(), rays_d=d.numpy(), loss=np.float64(loss.item()))
+    for k in helpers.GRAD_KEYS:
+        g = params[k].grad
+        out["grad_" + k] = g.numpy() if g.numel() < 20000 else g.numpy()[::7]
+        out["gnorm_" + k] = np.float64(g.double().norm().item())
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes; loss", loss.item())
+
+
 def main():
     cfg = synth.ModelConfig()
     make_case("scan63like_small", 4, 12, 12, cfg,
@@ -79,6 +108,7 @@ def main():
     cfg2 = synth.ModelConfig(enable_nablas_input=False, ln_s=0.4, learn_indicator_weight=True)
     make_case("nonabla_unbounded", 3, 10, 10, cfg2,
               dict(calc_normal=False, white_bkgd=False, bounded_near_far=False), seed=20)
+    make_train_case("train_step_small", 3, 48, seed=30)
 
 
 if __name__ == "__main__":

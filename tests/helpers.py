@@ -52,3 +52,42 @@ def sample_points(n, seed=0):
     radii = torch.cat([0.5 + 0.05 * torch.randn(k, generator=g), 0.15 + 1.2 * torch.rand(n - k, generator=g)])
     view = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1)
     return dirs * radii[:, None], view
+
+
+class OracleMeshGrid:
+    """TEST-ONLY stand-in for ``neumesh_b200.MeshGrid`` on CPU: same protocol, neighbour search by the oracle's exact
+    KNN.  Lets the differentiable torch-op path of ``neumesh_b200.NeuMesh`` / ``volume_render`` run without a GPU so
+    its gradients can be compared with the reference's autograd.  (The product has no CPU path.)"""
+
+    def __init__(self, mesh):
+        self.mesh = mesh
+        self.vertices = torch.as_tensor(np.asarray(mesh.vertices), dtype=torch.float32)
+        self.vertex_normals = torch.as_tensor(np.asarray(mesh.vertex_normals), dtype=torch.float32)
+        self.distance_method = "frnn"
+
+    def get_number_of_vertices(self):
+        return self.vertices.shape[0]
+
+    def get_vertex_normal_torch(self):
+        return self.vertex_normals
+
+    def get_vertices_torch(self):
+        return self.vertices
+
+    def compute_distance(self, xyz, indicator_vector=None, indicator_weight=0.1, K=8):
+        from oracle.field import mesh_distance
+        ind = self.vertex_normals if indicator_vector is None else indicator_vector
+        return mesh_distance(xyz, self.vertices, ind, indicator_weight, K)
+
+
+def train_loss(rgb, depth, extras):
+    """A scalar that touches everything the Trainer's losses touch (models/trainer.py:197-262): colour, mask/depth and
+    the eikonal term on ``implicit_nablas`` (which needs the double backward through the geometry MLP)."""
+    nab = extras["implicit_nablas"]
+    eik = ((nab.norm(dim=-1) - 1.0) ** 2).mean()
+    return rgb.mean() + 0.5 * extras["mask_volume"].mean() + 0.1 * depth.mean() + 0.1 * eik
+
+
+TRAIN_KW = dict(calc_normal=True, white_bkgd=False, bounded_near_far=True, detailed_output=True, perturb=False)
+GRAD_KEYS = ["geometry_features", "color_features", "indicator_vector", "ln_s", "pts_linears.0.weight_v",
+             "pts_linears.2.0.weight_g", "density_linear.weight_v", "views_linears.0.weight", "color_linear.0.bias"]
