@@ -179,6 +179,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="rays per kernel chunk (0 = library default)")
     ap.add_argument("--ref-rays", type=int, default=1024, help="rays per step of the CPU reference arm")
     ap.add_argument("--cpu-rays", type=int, default=1536, help="rays of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--all-samples", action="store_true",
+                    help="evaluate colour / nabla at every sample like the reference does, instead of only where the "
+                         "visibility weight is non-zero (bit-identical outputs either way)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -211,9 +214,10 @@ def main():
     resident = [(o[lo:hi].to(dev), d[lo:hi].to(dev)) for o, d in frames]
     chunk = args.chunk or None
 
-    def step_resident(i):
+    def step_resident(i, skip=None):
         o, d = resident[i % len(resident)]
-        part = render_fused(o, d, model, chunk=chunk, **RENDER_KW)
+        part = render_fused(o, d, model, chunk=chunk, skip_dead_samples=(not args.all_samples) if skip is None else skip,
+                            **RENDER_KW)
         return parallel.gather_image(part, n_rays, rank, world)
 
     def barrier():
@@ -249,6 +253,20 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         ms_total = float(ms.item())
 
+        # ---------------- same frames with every sample evaluated (reference-style work), for transparency ----------------
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        step_resident(0, skip=False)
+        barrier()
+        g0.record()
+        for i in range(args.steps):
+            step_resident(args.warmup + i, skip=False)
+        g1.record()
+        barrier()
+        ms3 = torch.tensor([g0.elapsed_time(g1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms3, op=dist.ReduceOp.MAX)
+        ms_all = float(ms3.item())
+
         # ---------------- end to end through the public API with host buffers ----------------
         rgb_host = torch.empty(n_rays, 3).pin_memory()
         depth_host = torch.empty(n_rays).pin_memory()
@@ -257,10 +275,11 @@ def main():
             o_h, d_h = host[i % len(host)]
             o = o_h[lo:hi].to(dev, non_blocking=True)
             d = d_h[lo:hi].to(dev, non_blocking=True)
-            if world == 1:
+            if world == 1 and not args.all_samples:
                 rgb, depth, _ = nb.volume_render(o, d, model, detailed_output=False, **RENDER_KW)
             else:
-                full = parallel.render_sharded_local(o, d, model, n_rays, rank, world, chunk=chunk, **RENDER_KW)
+                full = parallel.render_sharded_local(o, d, model, n_rays, rank, world, chunk=chunk,
+                                                     skip_dead_samples=not args.all_samples, **RENDER_KW)
                 rgb, depth = full["rgb"], full["depth_volume"]
             if rank == 0:
                 rgb_host.copy_(rgb, non_blocking=True)
@@ -297,32 +316,56 @@ def main():
             if k in kern and kern[k]["ms_per_step"] > 0:
                 kern[k]["gbs_algorithmic"] = kern[k]["points_per_step"] * BYTES_KNN / (kern[k]["ms_per_step"] * 1e-3) / 1e9
         mlp = [k for k in ("geo", "geo_jvp", "color") if k in kern]
-        dom = max(mlp, key=lambda k: kern[k]["ms_per_step"]) if mlp else None
-        roofline = None
-        if dom:
+        walk = [k for k in ("knn", "bound_scan") if k in kern]
+        kname = {"geo": "mlp_tc_kernel<0> (geometry MLP)", "geo_jvp": "mlp_tc_kernel<1> (geometry MLP + tangent rows)",
+                 "color": "mlp_tc_kernel<2> (colour MLP)", "knn": "knn_rays_kernel / knn_distance_kernel (8-NN walk + "
+                 "mesh distance)", "bound_scan": "bound_rays_kernel (bounded near/far scan)"}
+
+        def tensor_roofline(k):
             peak = peaks["bf16_tflops_sustained"]
-            ach = kern[dom]["tflops_algorithmic"]
-            traffic = None
-            tpath = os.path.join(ROOT, "profiles", "traffic.json")
-            if os.path.exists(tpath):
-                try:
-                    traffic = json.load(open(tpath)).get(dom)
-                except Exception:
-                    traffic = None
-            roofline = {"bound": "tensor", "kernel": f"mlp_tc_kernel<{dom}>", "achieved": ach, "peak": peak,
-                        "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
-                        "peak_source": f"{peaks['source']} dense bf16 cuBLAS, sustained",
-                        "note": "achieved = algorithmic fp32-equivalent FLOPs (each MAC once, reference dims) / device "
-                                "time of the kernel class; the kernel issues every MAC 3x as kind::tf32 (3xTF32 split), "
-                                "and TF32 runs at half the bf16 rate, so issued-TF32 utilisation of the TF32 pipe is "
-                                "6x this fraction",
-                        "mlp_ms_per_step": sum(kern[k]["ms_per_step"] for k in mlp),
-                        "avg_launch_ms": kern[dom]["ms_per_step"] / kern[dom]["launches_per_step"]}
-            if "knn" in kern:
-                roofline["knn_hbm"] = {"achieved_gbs": kern["knn"].get("gbs_algorithmic"), "peak_gbs": peaks["hbm_gbs"],
-                                       "frac": kern["knn"].get("gbs_algorithmic", 0) / peaks["hbm_gbs"],
-                                       "note": "octree walk over an L2-resident index (2.6 MB points + nodes): "
-                                               "latency/issue bound, not HBM bound"}
+            ach = kern[k]["tflops_algorithmic"]
+            return {"bound": "tensor", "kernel": kname[k], "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                    "frac": ach / peak, "traffic": traffic_of(k),
+                    "peak_source": f"{peaks['source']} dense bf16 cuBLAS, sustained",
+                    "avg_launch_ms": kern[k]["ms_per_step"] / kern[k]["launches_per_step"],
+                    "ms_per_step": kern[k]["ms_per_step"],
+                    "note": "achieved = algorithmic fp32-equivalent FLOPs (each MAC once, reference dims) / device time "
+                            "of the kernel class; the kernel issues every MAC 3x as kind::tf32 (3xTF32 split, needed "
+                            "for the 1e-4/1e-5 parity bar) and TF32 runs at half the bf16 rate, so the ceiling of this "
+                            "fraction is 1/6 = 0.167 x (MMA shape efficiency); tensor-pipe active is ~60 % (ncu)"}
+
+        def hbm_roofline(k):
+            ach = kern[k]["gbs_algorithmic"]
+            return {"bound": "hbm", "kernel": kname[k], "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm_gbs"], "traffic": traffic_of(k),
+                    "peak_source": f"{peaks['source']} copy bandwidth",
+                    "avg_launch_ms": kern[k]["ms_per_step"] / kern[k]["launches_per_step"],
+                    "ms_per_step": kern[k]["ms_per_step"],
+                    "note": "achieved = 204 algorithmic bytes per query (xyz + 8 x (vertex + indicator)) x queries / "
+                            "device time.  The octree index (5.9 MB) is L2-resident and the walk is a divergent, "
+                            "latency-bound pointer chase (ncu: DRAM < 1 %, SIMT efficiency 6-8 of 32 lanes, "
+                            "long_scoreboard dominant): HBM bandwidth is the nominal roofline for a gather, not the "
+                            "binding limit here"}
+
+        traffic_tab = {}
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic_tab = json.load(open(tpath))
+            except Exception:
+                traffic_tab = {}
+
+        def traffic_of(k):
+            return traffic_tab.get(k)
+
+        roofline = None
+        allk = mlp + walk
+        if allk:
+            dom = max(allk, key=lambda k: kern[k]["ms_per_step"])
+            roofline = tensor_roofline(dom) if dom in mlp else hbm_roofline(dom)
+            roofline["by_class"] = {k: (tensor_roofline(k) if k in mlp else hbm_roofline(k)) for k in allk}
+            for v in roofline["by_class"].values():
+                v.pop("note", None)
         cpu = None
         if world == 1 and args.cpu_rays > 0:
             rate, secs = cpu_oracle_rate(cfg, mesh, sd, frames[0][0], frames[0][1], args.cpu_rays)
@@ -337,11 +380,17 @@ def main():
             "scaling": "strong", "vs_baseline": None,
             "dtype": "fp32 (MLPs: 3xTF32 tcgen05, fp32 accumulate)" if args.engine == "tcgen05" else "fp32",
             "data": "synthetic", "config": {**workload_config(n_rays), "parallelism": f"ray-shard x{world} + all_gather",
-                                            "mlp_engine": args.engine},
+                                            "mlp_engine": args.engine,
+                                            "skip_dead_samples": not args.all_samples},
             "e2e": {"value": e2e_val, "unit": "rays/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": bo, "d2h_bytes_per_step": bi,
                     "api": "neumesh_b200.volume_render on pinned host rays; rgb + depth read back to pinned host"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kern,
+            "all_samples": {"value": n_rays * args.steps / (ms_all * 1e-3), "unit": "rays/s",
+                            "ms_per_step": ms_all / args.steps,
+                            "note": "same frames with colour / nabla evaluated at EVERY sample as the reference does "
+                                    "(skip_dead_samples=False); outputs are bit-identical to the default path, which "
+                                    "evaluates them only where the visibility weight is not exactly 0"},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

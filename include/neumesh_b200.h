@@ -118,6 +118,9 @@ typedef struct nmb_render_cfg {
   int32_t use_far_bypass;
   float far_bypass;
   int32_t normalize_dirs;     /* 1: apply F.normalize to rays_d (renderer.py:153) */
+  int32_t skip_dead_samples;  /* 1: evaluate colour / mid-point nabla / normals only at samples whose visibility weight
+                                 is not exactly 0 (the others are multiplied by 0.0f in renderer.py:304-333, so rgb, depth,
+                                 acc and normals are bit-identical); ignored when per-sample detail outputs are requested */
 } nmb_render_cfg;
 
 /* optional per-sample outputs (renderer.py:335-348, detailed_output=True); any pointer may be NULL.

@@ -33,6 +33,7 @@ class RenderCfg(C.Structure):
         ("N_upsample_iters", C.c_int32), ("bounded_near_far", C.c_int32), ("calc_normal", C.c_int32),
         ("white_bkgd", C.c_int32), ("use_near_bypass", C.c_int32), ("near_bypass", C.c_float),
         ("use_far_bypass", C.c_int32), ("far_bypass", C.c_float), ("normalize_dirs", C.c_int32),
+        ("skip_dead_samples", C.c_int32),
     ]
 
 

@@ -283,6 +283,122 @@ composite_kernel(int64_t R, int P, float s, int white_bkgd, const float* __restr
   }
 }
 
+// ---- live-sample path (cfg.skip_dead_samples) ---------------------------------------------------------------
+// The reference multiplies every mid-point colour, depth and point normal by its visibility weight
+// (renderer.py:304-333).  Where that weight is exactly 0.0f - in front of the shell (sigmoid saturates to 1), behind
+// the surface (transmittance underflows), on rays that miss - the colour MLP, the mid-point nabla and the KNN walk
+// feeding them cannot influence any composited output.  The kernels below compute the weights first, compact the
+// samples with a non-zero weight and evaluate only those; the composite then adds exactly the same non-zero terms
+// in the same order, so rgb / depth / acc / normals are bit-identical to evaluating everything.
+
+// pass 1 of the compositing: weights (same arithmetic as composite_kernel) + number of live samples per ray
+__global__ void __launch_bounds__(RT)
+weights_kernel(int64_t R, int P, float s, const float* __restrict__ sdf, float* __restrict__ wbuf,
+               int32_t* __restrict__ nlive) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  float c0 = sigmoid_t(__fmul_rn(sdf[r], s));
+  float T = 1.0f;
+  int n = 0;
+  for (int j = 0; j + 1 < P; ++j) {
+    const int64_t q = (int64_t)j * R + r;
+    const float c1 = sigmoid_t(__fmul_rn(sdf[q + R], s));
+    const float alpha = fmaxf(__fdiv_rn(__fsub_rn(c0, c1), __fadd_rn(c0, 1e-10f)), 0.f);
+    const float w = __fmul_rn(alpha, T);
+    T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f));
+    wbuf[q] = w;
+    n += (w != 0.f) ? 1 : 0;
+    c0 = c1;
+  }
+  nlive[r] = n;
+}
+
+// compact the live samples of every ray: mid-point position + view direction (+ sample position for the normals)
+__global__ void __launch_bounds__(RT)
+compact_live_kernel(int64_t R, int P, const int32_t* __restrict__ off, const float* __restrict__ wbuf,
+                    const float* __restrict__ z, const float* __restrict__ zmid, const float* __restrict__ orig,
+                    const float* __restrict__ dirs, float* __restrict__ xyz_mid, float* __restrict__ dir_live,
+                    float* __restrict__ xyz_pt /*nullable*/) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float ox = orig[r * 3], oy = orig[r * 3 + 1], oz = orig[r * 3 + 2];
+  const float dx = dirs[r * 3], dy = dirs[r * 3 + 1], dz = dirs[r * 3 + 2];
+  int64_t k = off[r];
+  for (int j = 0; j + 1 < P; ++j) {
+    const int64_t q = (int64_t)j * R + r;
+    if (wbuf[q] != 0.f) {
+      const float zm = zmid[q];
+      xyz_mid[k * 3 + 0] = __fadd_rn(ox, __fmul_rn(zm, dx));
+      xyz_mid[k * 3 + 1] = __fadd_rn(oy, __fmul_rn(zm, dy));
+      xyz_mid[k * 3 + 2] = __fadd_rn(oz, __fmul_rn(zm, dz));
+      dir_live[k * 3 + 0] = dx;
+      dir_live[k * 3 + 1] = dy;
+      dir_live[k * 3 + 2] = dz;
+      if (xyz_pt) {
+        const float zp = z[q];
+        xyz_pt[k * 3 + 0] = __fadd_rn(ox, __fmul_rn(zp, dx));
+        xyz_pt[k * 3 + 1] = __fadd_rn(oy, __fmul_rn(zp, dy));
+        xyz_pt[k * 3 + 2] = __fadd_rn(oz, __fmul_rn(zp, dz));
+      }
+      ++k;
+    }
+  }
+}
+
+// pass 2 of the compositing over the live samples only (same operation order as composite_kernel)
+__global__ void __launch_bounds__(RT)
+composite_live_kernel(int64_t R, int P, int white_bkgd, const float* __restrict__ wbuf, const float* __restrict__ zmid,
+                      const int32_t* __restrict__ off, const float* __restrict__ rgb_l /*[3][M]*/, int64_t M,
+                      const float* __restrict__ nabla_l /*[3][M] or null*/, const int32_t* __restrict__ perm,
+                      float* __restrict__ rgb_out, float* __restrict__ depth_out, float* __restrict__ acc_out,
+                      float* __restrict__ normals_out) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int64_t dst = perm[r];
+  float acc = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+  int64_t k = off[r];
+  for (int j = 0; j + 1 < P; ++j) {
+    const float w = wbuf[(int64_t)j * R + r];
+    if (w != 0.f) {
+      acc = __fadd_rn(acc, w);
+      cr = __fadd_rn(cr, __fmul_rn(w, rgb_l[k]));
+      cg = __fadd_rn(cg, __fmul_rn(w, rgb_l[M + k]));
+      cb = __fadd_rn(cb, __fmul_rn(w, rgb_l[2 * M + k]));
+      if (nabla_l) {
+        const float gx = nabla_l[k], gy = nabla_l[M + k], gz = nabla_l[2 * M + k];
+        const float nn = fmaxf(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz))), 1e-12f);
+        nx = __fadd_rn(nx, __fmul_rn(__fdiv_rn(gx, nn), w));
+        ny = __fadd_rn(ny, __fmul_rn(__fdiv_rn(gy, nn), w));
+        nz = __fadd_rn(nz, __fmul_rn(__fdiv_rn(gz, nn), w));
+      }
+      ++k;
+    }
+  }
+  const float den = __fadd_rn(acc, 1e-10f);
+  float depth = 0.f;
+  for (int j = 0; j + 1 < P; ++j) {
+    const int64_t q = (int64_t)j * R + r;
+    const float w = wbuf[q];
+    if (w != 0.f) depth = __fadd_rn(depth, __fmul_rn(__fdiv_rn(w, den), zmid[q]));
+  }
+  if (white_bkgd) {
+    const float bg = __fsub_rn(1.0f, acc);
+    cr = __fadd_rn(cr, bg);
+    cg = __fadd_rn(cg, bg);
+    cb = __fadd_rn(cb, bg);
+  }
+  rgb_out[dst * 3] = cr;
+  rgb_out[dst * 3 + 1] = cg;
+  rgb_out[dst * 3 + 2] = cb;
+  depth_out[dst] = depth;
+  acc_out[dst] = acc;
+  if (normals_out) {
+    normals_out[dst * 3] = nx;
+    normals_out[dst * 3 + 1] = ny;
+    normals_out[dst * 3 + 2] = nz;
+  }
+}
+
 // [S][R] sample-major -> [R,S] row-major (detail outputs); C channels with source stride cstride: out [R,S,C]
 __global__ void export_samples_kernel(int64_t R, int S, int C, const float* __restrict__ src, int64_t cstride,
                                       const int32_t* __restrict__ perm, float* __restrict__ dst) {
@@ -336,6 +452,10 @@ struct Workspace {
   float *k_ds, *k_w, *k_grad;
   int32_t* k_slot;
   float *nabla_pts, *nabla_mid, *sdf_mid, *rgb;
+  float *live_mid, *live_dir, *live_pt;   // [M,3] positions / directions of the live samples (M <= (P-1) R)
+  int32_t *nlive, *live_off;
+  void* scan_tmp;
+  int64_t scan_bytes;
   int64_t total;
 };
 
@@ -369,6 +489,13 @@ Workspace carve(void* base, int64_t R, int P, int n_new) {
   w.nabla_mid = take(3 * PR);
   w.sdf_mid = take(PR);
   w.rgb = take(3 * PR);
+  w.live_mid = take(3 * PR);
+  w.live_dir = take(3 * PR);
+  w.live_pt = take(3 * PR);
+  w.nlive = reinterpret_cast<int32_t*>(take(R));
+  w.live_off = reinterpret_cast<int32_t*>(take(R + 1));
+  w.scan_bytes = 16 * 1024 + R / 32;   // cub::DeviceScan temp storage (a few KB; generous)
+  w.scan_tmp = take(w.scan_bytes / 4 + 1);
   w.total = off;
   return w;
 }
@@ -474,8 +601,10 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
     // their sdf is already known (same point, same kernel => same bits) and, with calc_normal, the nabla is obtained
     // in those passes too (tangent rows) and carried through the merges: no second KNN walk, no second MLP pass.
     const int64_t PR = (int64_t)P * R;
-    float* nab_pts = cfg->calc_normal ? w.nabla_pts : nullptr;
-    float* nab_new = cfg->calc_normal ? w.nabla_mid : nullptr;   // free until the mid-point pass
+    const bool live_path = cfg->skip_dead_samples && !detail;
+    // full path: nabla at every sample comes from the sampling passes; live path: only where the weight is non-zero
+    float* nab_pts = (cfg->calc_normal && !live_path) ? w.nabla_pts : nullptr;
+    float* nab_new = (cfg->calc_normal && !live_path) ? w.nabla_mid : nullptr;   // free until the mid-point pass
     int rc = eval(w.z, n, w.sdf, nab_pts, false);
     if (rc) return rc;
     for (int it = 0; it < n_iters; ++it) {
@@ -490,6 +619,59 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
     midpoints_kernel<<<(unsigned)ceil_div(R * (P - 1), 256), 256, 0, stream>>>(R, P, w.z, w.zmid);
     NMB_LAUNCH_OK();
     const bool need_mid_nabla = f->lay.use_nabla != 0;
+    if (live_path) {
+      // weights first, then only the samples that can contribute
+      weights_kernel<<<rb, RT, 0, stream>>>(R, P, f->s, w.sdf, w.wbuf, w.nlive);
+      NMB_LAUNCH_OK();
+      size_t need = 0;
+      NMB_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, need, w.nlive, w.live_off, (int)R, stream));
+      NMB_CHECK((int64_t)need <= w.scan_bytes, "scan scratch too small");
+      size_t sb = (size_t)w.scan_bytes;
+      NMB_CUDA_OK(cub::DeviceScan::ExclusiveSum(w.scan_tmp, sb, w.nlive, w.live_off, (int)R, stream));
+      count_launch(2);
+      int32_t last_off = 0, last_n = 0;
+      NMB_CUDA_OK(cudaMemcpyAsync(&last_off, w.live_off + (R - 1), 4, cudaMemcpyDeviceToHost, stream));
+      NMB_CUDA_OK(cudaMemcpyAsync(&last_n, w.nlive + (R - 1), 4, cudaMemcpyDeviceToHost, stream));
+      NMB_CUDA_OK(cudaStreamSynchronize(stream));
+      const int64_t M = (int64_t)last_off + last_n;
+      if (M > 0) {
+        compact_live_kernel<<<rb, RT, 0, stream>>>(R, P, w.live_off, w.wbuf, w.z, w.zmid, w.orig, w.dirs, w.live_mid,
+                                                   w.live_dir, cfg->calc_normal ? w.live_pt : nullptr);
+        NMB_LAUNCH_OK();
+        auto eval_list = [&](const float* xyz, float* sdf_out, float* nabla_out, bool color) -> int {
+          KnnOut ko{w.k_ds, w.k_slot, w.k_w, w.k_grad, M};
+          PointSrc src{xyz, nullptr, nullptr, nullptr, 0};
+          int rc2 = launch_knn_distance(g, f->indicator.p, f->w1, src, M, ko, stream);
+          if (rc2) return rc2;
+          FieldIn in{};
+          in.ds = ko.ds;
+          in.slot = ko.slot;
+          in.w = ko.w;
+          in.grad = ko.grad;
+          in.stride = M;
+          rc2 = launch_geo(f, in, M, sdf_out, nabla_out, stream);
+          if (rc2) return rc2;
+          if (color) {
+            in.nabla = nabla_out;
+            in.dirs = w.live_dir;
+            rc2 = launch_color(f, in, M, w.rgb, stream);
+            if (rc2) return rc2;
+          }
+          return 0;
+        };
+        rc = eval_list(w.live_mid, w.sdf_mid, need_mid_nabla ? w.nabla_mid : nullptr, true);
+        if (rc) return rc;
+        if (cfg->calc_normal) {
+          rc = eval_list(w.live_pt, w.sdf_mid, w.nabla_pts, false);
+          if (rc) return rc;
+        }
+      }
+      composite_live_kernel<<<rb, RT, 0, stream>>>(R, P, cfg->white_bkgd, w.wbuf, w.zmid, w.live_off, w.rgb, M,
+                                                   cfg->calc_normal ? w.nabla_pts : nullptr, perm, rgb, depth, acc,
+                                                   normals);
+      NMB_LAUNCH_OK();
+      continue;
+    }
     rc = eval(w.zmid, P - 1, w.sdf_mid, need_mid_nabla ? w.nabla_mid : nullptr, true);
     if (rc) return rc;
     composite_kernel<<<rb, RT, 0, stream>>>(R, P, f->s, cfg->white_bkgd, w.sdf, w.zmid, w.rgb, (int64_t)P * R,

@@ -51,7 +51,7 @@ def fused_eligible(model, rays_o, *, batched, perturb, random_color_direction, u
 def render_fused(rays_o, rays_d, model: NeuMesh, *, obj_bounding_radius=1.0, calc_normal=False, white_bkgd=False,
                  near_bypass=None, far_bypass=None, N_samples=64, N_importance=64, N_upsample_iters=4,
                  bounded_near_far=True, detailed_output=False, samples_output=False, chunk=None,
-                 normalize_dirs=True):
+                 normalize_dirs=True, skip_dead_samples=True):
     """Flat [N,3] rays -> dict of flat outputs, through ``nmb_render``."""
     dev = rays_o.device
     o = rays_o.detach().reshape(-1, 3).float().contiguous()
@@ -60,7 +60,8 @@ def render_fused(rays_o, rays_d, model: NeuMesh, *, obj_bounding_radius=1.0, cal
     cfg = _lib.RenderCfg(float(obj_bounding_radius), int(N_samples), int(N_importance), int(N_upsample_iters),
                          int(bool(bounded_near_far)), int(bool(calc_normal)), int(bool(white_bkgd)),
                          int(near_bypass is not None), float(near_bypass or 0.0), int(far_bypass is not None),
-                         float(far_bypass or 0.0), int(bool(normalize_dirs)))
+                         float(far_bypass or 0.0), int(bool(normalize_dirs)),
+                         int(bool(skip_dead_samples) and not detailed_output))
     chunk = int(min(chunk or DEFAULT_FUSED_CHUNK, max(N, 1)))
     field = model.packed_field()
     L = _lib.lib()

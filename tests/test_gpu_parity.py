@@ -435,10 +435,14 @@ def test_full_size_properties(engine):
         b = render_fused(o, d, model, chunk=8192, **kw)      # chunking changes no arithmetic
         perm = torch.randperm(o.shape[0], device=dev)
         c = render_fused(o[perm], d[perm], model, chunk=32768, **kw)  # rays are independent
+        # evaluating EVERY sample (as the reference does) instead of only those with a non-zero visibility weight
+        # adds exact zeros: bit-identical outputs
+        e = render_fused(o, d, model, chunk=100000, skip_dead_samples=False, **kw)
     for k in ("rgb", "depth_volume", "mask_volume", "normals_volume"):
         assert torch.isfinite(a[k]).all(), k
         assert torch.equal(a[k], b[k]), f"{k}: chunked render differs"
         assert torch.equal(a[k][perm], c[k]), f"{k}: permuted render differs"
+        assert torch.equal(a[k], e[k]), f"{k}: live-sample path differs from the all-samples path"
     acc = a["mask_volume"]
     assert acc.min() >= 0 and acc.max() <= 1 + 1e-4
     assert (a["rgb"] >= -1e-5).all() and (a["rgb"] <= 1 + 1e-4).all()
