@@ -132,6 +132,8 @@ static int pack_field(const nmb_field_desc* d, nmb_field* f, cudaStream_t stream
   NMB_CHECK(d->multires_d >= 0 && d->multires_fg >= 0 && d->multires_ft >= 0 && d->multires_view >= 0,
             "identity embedders (multires < 0) are not supported by the fused kernels");
   f->lay = make_layout(d);
+  f->shell_valid = false;
+  f->shell = ShellGrid{};
   NMB_CHECK(f->lay.K0g <= 256 && f->lay.K0c <= 256, "first-layer width exceeds the fused kernels' 256-column tile");
   f->w1 = d->indicator_weight;
   f->s = d->s;

@@ -50,6 +50,11 @@ struct nmb_field {
   nmb::DevBuf<float> fc;          // [V,32] sorted
   nmb::MlpFfma geo_f, col_f;
   nmb::MlpTc geo_t, col_t;
+  // shell-free certificate grid (built lazily by the first large render after a (re)pack; csrc/shell.cu)
+  mutable nmb::DevBuf<uint8_t> shell_cells;
+  mutable nmb::DevBuf<float4> node_normals;   // per octree node: mean indicator vector, max deviation
+  mutable bool shell_valid = false;
+  mutable nmb::ShellGrid shell{};
 };
 
 namespace nmb {
@@ -83,5 +88,7 @@ inline int launch_color(const nmb_field* f, const FieldIn& in, int64_t P, float*
 
 int permute_indicator(const nmb_grid* g, const float* indicator, float4* dst, cudaStream_t stream);
 int pack_mlp_tc(const nmb_field_desc* d, const FieldLayout& lay, nmb_field* f, cudaStream_t stream);
+// builds f->shell if it is not valid; on any failure leaves it empty (the scan then evaluates every sample)
+int ensure_shell_grid(const nmb_field* f, cudaStream_t stream);
 
 }  // namespace nmb

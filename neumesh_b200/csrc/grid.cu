@@ -357,6 +357,7 @@ static int build_grid(const float* vertices, int64_t V, cudaStream_t stream, nmb
     lvl_off.push_back(n_nodes);
   }
   g->num_nodes = n_nodes;
+  g->lvl_off = lvl_off;
   NMB_CUDA_OK(g->nodes.alloc(NODE_F4 * (int64_t)n_nodes));
   for (int l = (int)lvl_off.size() - 2; l >= 0; --l) {
     const int32_t first = lvl_off[l], cnt = lvl_off[l + 1] - lvl_off[l];
@@ -748,7 +749,8 @@ __global__ void __launch_bounds__(128)
 bound_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts,
                   const float4* __restrict__ indicator, float w1, const float* __restrict__ rays_o,
                   const float* __restrict__ dirs, const float* __restrict__ near, const float* __restrict__ far,
-                  int64_t R, int n_grid, float thresh, int32_t* __restrict__ bnear, int32_t* __restrict__ bfar) {
+                  int64_t R, int n_grid, float thresh, int32_t* __restrict__ bnear, int32_t* __restrict__ bfar,
+                  ShellGrid shell) {
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= R) return;
   const float ox = rays_o[r * 3 + 0], oy = rays_o[r * 3 + 1], oz = rays_o[r * 3 + 2];
@@ -756,12 +758,27 @@ bound_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ p
   const float nr = near[r], fr = far[r];
   float d2[KNN_K];
   int32_t ix[KNN_K];
-  auto ds_at = [&](int s, bool warm, float& depth) {
+  bool have_prev = false;   // d2 / ix hold the neighbours of some earlier sample of this ray (valid warm start)
+  // returns the mesh distance at sample s, or +inf when the sample lies in a cell certified to be outside the shell
+  auto ds_at = [&](int s, float& depth) {
     const float t = linspace01(s, n_grid);
     depth = __fadd_rn(__fmul_rn(nr, __fsub_rn(1.0f, t)), __fmul_rn(fr, t));  // renderer.py:81
     const float qx = __fadd_rn(ox, __fmul_rn(depth, dx));
     const float qy = __fadd_rn(oy, __fmul_rn(depth, dy));
     const float qz = __fadd_rn(oz, __fmul_rn(depth, dz));
+    if (shell.cells) {
+      const float sc = 0.5f * (float)shell.G / shell.B;
+      const float fx = (qx + shell.B) * sc, fy = (qy + shell.B) * sc, fz = (qz + shell.B) * sc;
+      if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)shell.G && fy < (float)shell.G && fz < (float)shell.G) {
+        const int64_t cell = ((int64_t)(int)fz * shell.G + (int)fy) * shell.G + (int)fx;
+        if (__ldg(shell.cells + cell)) return CUDART_INF_F;
+      } else {
+        const float ex = qx - shell.cx, ey = qy - shell.cy, ez = qz - shell.cz;
+        if (ex * ex + ey * ey + ez * ez >= shell.far_r * shell.far_r) return CUDART_INF_F;
+      }
+    }
+    const bool warm = have_prev;
+    have_prev = true;
     if (warm) {
       warm_rerank<KNN_K>(pts, qx, qy, qz, d2, ix);
       knn_walk<KNN_K, true>(nodes, pts, qx, qy, qz, d2, ix);
@@ -775,7 +792,7 @@ bound_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ p
   int first = -1;
   float depth = 0.f;
   for (int s = 0; s < n_grid; ++s) {
-    if (ds_at(s, s > 0, depth) < thresh) {
+    if (ds_at(s, depth) < thresh) {
       first = s;
       bnear[r] = __float_as_int(depth);
       break;
@@ -784,7 +801,7 @@ bound_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ p
   if (first < 0) return;  // no sample inside the shell: bnear / bfar keep their "unset" values
   for (int s = n_grid - 1; s >= first; --s) {
     // s == first is known to be a hit: the loop always terminates with bfar set
-    if (s == first || ds_at(s, s < n_grid - 1, depth) < thresh) {
+    if (s == first || ds_at(s, depth) < thresh) {
       if (s == first) {
         const float t = linspace01(s, n_grid);
         depth = __fadd_rn(__fmul_rn(nr, __fsub_rn(1.0f, t)), __fmul_rn(fr, t));
@@ -797,13 +814,14 @@ bound_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ p
 
 int launch_bound_scan(const nmb_grid* g, const float4* indicator, float w1, const float* rays_o, const float* dirs,
                       const float* near, const float* far, int64_t R, int n_grid, float thresh, int32_t* bnear,
-                      int32_t* bfar, cudaStream_t stream) {
+                      int32_t* bfar, ShellGrid shell, cudaStream_t stream) {
   const int64_t n = R * n_grid;
   if (n <= 0) return 0;
   ProfScope prof(PROF_BOUND, n, stream);
   if (R >= RAY_KERNEL_MIN_RAYS) {
     bound_rays_kernel<<<(unsigned)ceil_div(R, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator, w1, rays_o, dirs,
-                                                                     near, far, R, n_grid, thresh, bnear, bfar);
+                                                                     near, far, R, n_grid, thresh, bnear, bfar,
+                                                                     (thresh == 0.1f) ? shell : ShellGrid{});
     NMB_LAUNCH_OK();
     return 0;
   }

@@ -1,5 +1,7 @@
 // Spatial index over mesh vertices: Morton-ordered sparse octree with tight node boxes.
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 struct nmb_grid {
@@ -12,6 +14,7 @@ struct nmb_grid {
   nmb::DevBuf<int32_t> order;  // [V] sorted slot -> original index
   nmb::DevBuf<int32_t> inv;    // [V] original index -> sorted slot
   nmb::DevBuf<float4> nodes;   // [NODE_F4*num_nodes]: box + disc bounds and child / point links; see grid.cu
+  std::vector<int32_t> lvl_off; // first node id of every octree level (+ end sentinel); children ids > parent ids
 };
 
 namespace nmb {
@@ -47,9 +50,18 @@ __device__ __forceinline__ float linspace01(int i, int n) {
   return (i < n / 2) ? __fmul_rn(step, (float)i) : fmaf(-step, (float)(n - 1 - i), 1.0f);
 }
 
+// "Shell-free" certificate grid (csrc/shell.cu): cell (i,j,k) of a G^3 grid over [-B,B]^3 is 1 when EVERY point of the
+// cell provably has mesh distance ds >= 0.1 + margin, so the bounded-near/far scan may skip it without evaluating.
+struct ShellGrid {
+  const uint8_t* cells = nullptr;   // nullptr = no certificate available
+  int G = 0;
+  float B = 0.f;
+  float cx = 0.f, cy = 0.f, cz = 0.f, far_r = 0.f;   // |x - c| >= far_r  =>  certified as well (outside the grid)
+};
+
 int launch_bound_scan(const nmb_grid* g, const float4* indicator, float w1, const float* rays_o, const float* dirs,
                       const float* near, const float* far, int64_t R, int n_grid, float thresh, int32_t* bnear,
-                      int32_t* bfar, cudaStream_t stream);
+                      int32_t* bfar, ShellGrid shell, cudaStream_t stream);
 
 int launch_knn_distance(const nmb_grid* g, const float4* indicator_sorted, float w1, PointSrc src, int64_t P,
                         KnnOut out, cudaStream_t stream);

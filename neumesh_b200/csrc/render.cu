@@ -556,8 +556,14 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
                                             w.orig, w.dirs, w.near, w.far, w.bnear, w.bfar);
     NMB_LAUNCH_OK();
     if (cfg->bounded_near_far) {
+      ShellGrid shell{};
+      if (R >= 65536) {   // the certificate costs ~0.1-0.3 s to build: only worth it for frame-sized renders
+        int rcs = ensure_shell_grid(f, stream);
+        if (rcs) return rcs;
+        shell = f->shell;
+      }
       int rc = launch_bound_scan(g, f->indicator.p, f->w1, ro, w.dirs, w.near, w.far, R, 256, 0.1f, w.bnear, w.bfar,
-                                 stream);
+                                 shell, stream);
       if (rc) return rc;
       bound_finish_kernel<<<rb, RT, 0, stream>>>(R, w.bnear, w.bfar, w.near, w.far);
       NMB_LAUNCH_OK();

@@ -443,6 +443,14 @@ def test_full_size_properties(engine):
         assert torch.equal(a[k], b[k]), f"{k}: chunked render differs"
         assert torch.equal(a[k][perm], c[k]), f"{k}: permuted render differs"
         assert torch.equal(a[k], e[k]), f"{k}: live-sample path differs from the all-samples path"
+    # bounded near / far: the frame-sized launch uses the ray-ordered early-exit scan with the shell-free certificate
+    # grid (csrc/shell.cu); small chunks use the plain 256-sample scan.  Both must give the same bits on every ray.
+    with torch.no_grad():
+        nf_big = render_fused(o, d, model, chunk=100000, N_upsample_iters=0, N_importance=0, calc_normal=False,
+                              detailed_output=True)["near_far"]
+        nf_small = render_fused(o, d, model, chunk=8192, N_upsample_iters=0, N_importance=0, calc_normal=False,
+                                detailed_output=True)["near_far"]
+    assert torch.equal(nf_big, nf_small), "certificate / early-exit scan changed a near or far value"
     acc = a["mask_volume"]
     assert acc.min() >= 0 and acc.max() <= 1 + 1e-4
     assert (a["rgb"] >= -1e-5).all() and (a["rgb"] <= 1 + 1e-4).all()
