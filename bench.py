@@ -356,7 +356,11 @@ def main():
                 traffic_tab = {}
 
         def traffic_of(k):
-            return traffic_tab.get(k)
+            """DRAM bytes per launch: ncu-measured bytes per processed point x points per launch of this run."""
+            bpp = traffic_tab.get("bytes_per_point", {}).get(k)
+            if bpp is None or k not in kern or not kern[k]["launches_per_step"]:
+                return None
+            return bpp * kern[k]["points_per_step"] / kern[k]["launches_per_step"]
 
         roofline = None
         allk = mlp + walk

@@ -103,6 +103,11 @@ int nmb_field_sdf(const nmb_field* f, const float* xyz /*[M,3]*/, int64_t M, flo
 int nmb_field_forward(const nmb_field* f, const float* xyz, const float* view_dirs, int64_t M, float* sdf,
                       float* rgb, float* nabla, void* stream);
 
+/* Shell-free certificate grid used by nmb_render's bounded near/far scan (csrc/shell.cu): builds it if necessary and
+ * copies the G^3 bytes to `cells` (device, may be NULL to query the size only).  cells[(z*G + y)*G + x] == 1 means:
+ * every point of that cell of the grid over [-B, B]^3 provably has mesh distance ds >= 0.1.  Returns G and B. */
+int nmb_field_shell_grid(const nmb_field* f, uint8_t* cells, int32_t* G, float* B, void* stream);
+
 /* ---- renderer ------------------------------------------------------------------------------------------------
  * volume_render (models/renderer.py:105-368), un-batched, perturb=False, no grad. */
 typedef struct nmb_render_cfg {

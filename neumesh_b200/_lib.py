@@ -61,6 +61,7 @@ SIGNATURES = {
     "nmb_field_create": (C.c_int, [_P, C.POINTER(FieldDesc), C.c_int, _P, C.POINTER(_P)]),
     "nmb_field_destroy": (None, [_P]),
     "nmb_field_update": (C.c_int, [_P, C.POINTER(FieldDesc), _P]),
+    "nmb_field_shell_grid": (C.c_int, [_P, _P, C.POINTER(_I32), C.POINTER(_F), _P]),
     "nmb_field_sdf": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
     "nmb_field_forward": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P]),
     "nmb_render_workspace_bytes": (_I64, [C.POINTER(RenderCfg), _I64]),

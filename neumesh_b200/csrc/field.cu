@@ -235,6 +235,20 @@ static int field_query(const nmb_field* f, const float* xyz, const float* dirs, 
   return 0;
 }
 
+int nmb_field_shell_grid(const nmb_field* f, uint8_t* cells, int32_t* G, float* B, void* stream_) {
+  NMB_CHECK(f != nullptr && G != nullptr && B != nullptr, "null argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = nmb::ensure_shell_grid(f, stream);
+  if (rc) return rc;
+  *G = f->shell.G;
+  *B = f->shell.B;
+  if (cells && f->shell.cells) {
+    NMB_CUDA_OK(cudaMemcpyAsync(cells, f->shell.cells, (size_t)f->shell.G * f->shell.G * f->shell.G,
+                                cudaMemcpyDeviceToDevice, stream));
+  }
+  return 0;
+}
+
 int nmb_field_sdf(const nmb_field* f, const float* xyz, int64_t M, float* sdf, float* nabla, void* stream) {
   return field_query(f, xyz, nullptr, M, sdf, nullptr, nabla, false, static_cast<cudaStream_t>(stream));
 }

@@ -696,6 +696,54 @@ knn_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts
   }
 }
 
+// Per-ray lists of explicit points (the compacted live samples of nmb_render): thread r walks its entries
+// [off[r], off[r] + cnt[r]) in order - they are consecutive samples of one ray - warm-starting each query with the
+// previous one's neighbours.
+__global__ void __launch_bounds__(128)
+knn_lists_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts, const float4* __restrict__ indicator,
+                 float w1, const float* __restrict__ xyz, const int32_t* __restrict__ off,
+                 const int32_t* __restrict__ cnt, int64_t R, KnnOut out) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int64_t b = off[r];
+  const int n = cnt[r];
+  float d2[KNN_K];
+  int32_t ix[KNN_K];
+  for (int j = 0; j < n; ++j) {
+    const int64_t p = b + j;
+    const float qx = xyz[p * 3], qy = xyz[p * 3 + 1], qz = xyz[p * 3 + 2];
+    if (j == 0) {
+      knn_walk<KNN_K, false>(nodes, pts, qx, qy, qz, d2, ix);
+    } else {
+      warm_rerank<KNN_K>(pts, qx, qy, qz, d2, ix);
+      knn_walk<KNN_K, true>(nodes, pts, qx, qy, qz, d2, ix);
+    }
+    float w[KNN_K], ds, grad[3];
+    mesh_distance_point(pts, indicator, w1, qx, qy, qz, d2, ix, w, ds, grad);
+    out.ds[p] = ds;
+#pragma unroll
+    for (int k = 0; k < KNN_K; ++k) {
+      out.slot[k * out.stride + p] = ix[k];
+      out.w[k * out.stride + p] = w[k];
+    }
+    if (out.grad) {
+      out.grad[0 * out.stride + p] = grad[0];
+      out.grad[1 * out.stride + p] = grad[1];
+      out.grad[2 * out.stride + p] = grad[2];
+    }
+  }
+}
+
+int launch_knn_lists(const nmb_grid* g, const float4* indicator_sorted, float w1, const float* xyz, const int32_t* off,
+                     const int32_t* cnt, int64_t R, int64_t M, KnnOut out, cudaStream_t stream) {
+  if (M <= 0 || R <= 0) return 0;
+  ProfScope prof(PROF_KNN, M, stream);
+  knn_lists_kernel<<<(unsigned)ceil_div(R, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, xyz, off,
+                                                                  cnt, R, out);
+  NMB_LAUNCH_OK();
+  return 0;
+}
+
 constexpr int64_t RAY_KERNEL_MIN_RAYS = 32768;  // below this the per-point kernels expose more parallelism
 
 int launch_knn_distance(const nmb_grid* g, const float4* indicator_sorted, float w1, PointSrc src, int64_t P,

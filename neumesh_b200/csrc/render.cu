@@ -646,8 +646,13 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
         NMB_LAUNCH_OK();
         auto eval_list = [&](const float* xyz, float* sdf_out, float* nabla_out, bool color) -> int {
           KnnOut ko{w.k_ds, w.k_slot, w.k_w, w.k_grad, M};
-          PointSrc src{xyz, nullptr, nullptr, nullptr, 0};
-          int rc2 = launch_knn_distance(g, f->indicator.p, f->w1, src, M, ko, stream);
+          int rc2;
+          if (R >= 32768) {   // enough rays to fill the GPU with one thread per ray: warm-started per-ray lists
+            rc2 = launch_knn_lists(g, f->indicator.p, f->w1, xyz, w.live_off, w.nlive, R, M, ko, stream);
+          } else {
+            PointSrc src{xyz, nullptr, nullptr, nullptr, 0};
+            rc2 = launch_knn_distance(g, f->indicator.p, f->w1, src, M, ko, stream);
+          }
           if (rc2) return rc2;
           FieldIn in{};
           in.ds = ko.ds;

@@ -164,6 +164,21 @@ class NeuMesh(nn.Module):
         self._field_key = key
         return self._field
 
+    def shell_free_grid(self):
+        """(cells [G,G,G] uint8 CUDA tensor indexed [z,y,x], B): cells == 1 where every point of the cell of the grid
+        over [-B,B]^3 provably has mesh distance >= 0.1 (the certificate the bounded near/far scan skips by)."""
+        field = self.packed_field()
+        dev = self.geometry_features.device
+        G, B = C.c_int32(0), C.c_float(0.0)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().nmb_field_shell_grid(field, None, C.byref(G), C.byref(B), _lib.stream_ptr(dev)))
+            cells = torch.zeros(max(G.value, 1) ** 3, dtype=torch.uint8, device=dev)
+            if G.value > 0:
+                _lib.check(_lib.lib().nmb_field_shell_grid(field, _lib.ptr(cells), C.byref(G), C.byref(B),
+                                                           _lib.stream_ptr(dev)))
+        g = max(G.value, 1)
+        return cells.reshape(g, g, g), float(B.value)
+
     def _release_field(self):
         h = self.__dict__.get("_field")
         self.__dict__["_field"] = None   # plain attribute: bypass nn.Module.__setattr__ (safe at interpreter exit)

@@ -470,6 +470,35 @@ def test_full_size_properties(engine):
     assert torch.isfinite(m["rgb"]).all()
 
 
+@pytest.mark.parametrize("learn_w", [False, True])
+def test_shell_certificate_is_sound(learn_w):
+    """Every point of a cell the certificate grid marks must really have ds >= 0.1 (renderer.py:87 threshold)."""
+    dev = _dev()
+    cfg = synth.ModelConfig(learn_indicator_weight=learn_w)
+    mesh = synth.icosphere_mesh(6, seed=4)
+    sd = synth.make_state_dict(mesh, cfg, seed=5)
+    sd["indicator_vector"] = sd["indicator_vector"] * (1.0 + 0.3 * torch.rand(sd["indicator_vector"].shape[0], 1))
+    model = helpers.cuda_model(mesh, cfg, sd, "fp32")
+    cells, B = model.shell_free_grid()
+    G = cells.shape[0]
+    assert G > 1
+    frac = cells.float().mean().item()
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x = ((torch.rand(3_000_000, 3, generator=g) * 2 - 1) * B * 0.9999).to(dev)
+    ijk = ((x + B) * (0.5 * G / B)).long().clamp_(0, G - 1)
+    marked = cells[ijk[:, 2], ijk[:, 1], ijk[:, 0]].bool()
+    with torch.no_grad():
+        ds, _, _ = model.compute_distance(x[marked])
+    print(f"certified cells {frac:.3f}; sampled points in certified cells {int(marked.sum())}; "
+          f"min ds among them {ds.min().item():.4f}")
+    assert marked.float().mean() > 0.2, "certificate should cover a sizeable part of the volume"
+    assert ds.min().item() >= 0.1
+    # and it is not vacuous: cells near the surface are left unmarked
+    near = torch.from_numpy(mesh.vertices[:2000]).float().to(dev)
+    ijk = ((near + B) * (0.5 * G / B)).long().clamp_(0, G - 1)
+    assert not cells[ijk[:, 2], ijk[:, 1], ijk[:, 0]].any()
+
+
 def test_get_rays_matches_synth():
     from neumesh_b200.renderer import get_rays
     dev = _dev()
