@@ -312,14 +312,23 @@ def main():
         for k, fl in flops.items():
             if k in kern and kern[k]["ms_per_step"] > 0:
                 kern[k]["tflops_algorithmic"] = kern[k]["points_per_step"] * fl / (kern[k]["ms_per_step"] * 1e-3) / 1e12
-        for k in ("knn", "bound_scan"):
+        for k in ("knn", "bound_scan", "knn_list"):
             if k in kern and kern[k]["ms_per_step"] > 0:
                 kern[k]["gbs_algorithmic"] = kern[k]["points_per_step"] * BYTES_KNN / (kern[k]["ms_per_step"] * 1e-3) / 1e9
         mlp = [k for k in ("geo", "geo_jvp", "color") if k in kern]
-        walk = [k for k in ("knn", "bound_scan") if k in kern]
+        walk = [k for k in ("knn", "knn_list", "bound_scan") if k in kern]
+        if mlp:   # the three instantiations of the ONE tcgen05 kernel template, taken together
+            tot_ms = sum(kern[k]["ms_per_step"] for k in mlp)
+            tot_fl = sum(kern[k]["points_per_step"] * flops[k] for k in mlp)
+            kern["mlp_tc"] = {"ms_per_step": tot_ms, "launches_per_step": sum(kern[k]["launches_per_step"] for k in mlp),
+                              "points_per_step": sum(kern[k]["points_per_step"] for k in mlp),
+                              "tflops_algorithmic": tot_fl / (tot_ms * 1e-3) / 1e12}
+            mlp = mlp + ["mlp_tc"]
         kname = {"geo": "mlp_tc_kernel<0> (geometry MLP)", "geo_jvp": "mlp_tc_kernel<1> (geometry MLP + tangent rows)",
-                 "color": "mlp_tc_kernel<2> (colour MLP)", "knn": "knn_rays_kernel / knn_distance_kernel (8-NN walk + "
-                 "mesh distance)", "bound_scan": "bound_rays_kernel (bounded near/far scan)"}
+                 "color": "mlp_tc_kernel<2> (colour MLP)", "mlp_tc": "mlp_tc_kernel<0|1|2> (tcgen05 field MLPs, all "
+                 "instantiations)", "knn": "knn_rays_kernel (8-NN walk + mesh distance, ray-ordered)",
+                 "knn_list": "knn_lists_kernel (8-NN walk + mesh distance, live samples)",
+                 "bound_scan": "bound_rays_kernel (bounded near/far scan)"}
 
         def tensor_roofline(k):
             peak = peaks["bf16_tflops_sustained"]
@@ -357,7 +366,13 @@ def main():
 
         def traffic_of(k):
             """DRAM bytes per launch: ncu-measured bytes per processed point x points per launch of this run."""
-            bpp = traffic_tab.get("bytes_per_point", {}).get(k)
+            tab = traffic_tab.get("bytes_per_point", {})
+            if k == "mlp_tc":
+                parts = [kk for kk in ("geo", "geo_jvp", "color") if kk in kern and kk in tab]
+                if not parts:
+                    return None
+                return sum(tab[kk] * kern[kk]["points_per_step"] for kk in parts) / kern[k]["launches_per_step"]
+            bpp = tab.get("knn" if k == "knn_list" else k)
             if bpp is None or k not in kern or not kern[k]["launches_per_step"]:
                 return None
             return bpp * kern[k]["points_per_step"] / kern[k]["launches_per_step"]
@@ -365,7 +380,8 @@ def main():
         roofline = None
         allk = mlp + walk
         if allk:
-            dom = max(allk, key=lambda k: kern[k]["ms_per_step"])
+            cand = [k for k in allk if k not in ("geo", "geo_jvp", "color")]   # MLP instantiations count once, together
+            dom = max(cand, key=lambda k: kern[k]["ms_per_step"])
             roofline = tensor_roofline(dom) if dom in mlp else hbm_roofline(dom)
             roofline["by_class"] = {k: (tensor_roofline(k) if k in mlp else hbm_roofline(k)) for k in allk}
             for v in roofline["by_class"].values():

@@ -37,7 +37,8 @@ int64_t nmb_launch_count(void);
 
 /* Per-kernel-class device timing for roofline reports (bench.py): when enabled, CUDA events are recorded on the
  * launching stream around every launch of a class; collect() synchronises those events and returns, per class
- * {0 knn+distance, 1 bounded-near/far scan, 2 geometry MLP, 3 geometry MLP + tangents, 4 colour MLP, 5 samplers},
+ * {0 knn+distance (ray-ordered / per-point), 1 bounded-near/far scan, 2 geometry MLP, 3 geometry MLP + tangents,
+ *  4 colour MLP, 5 samplers (unused), 6 knn+distance over per-ray lists of live samples},
  * the summed milliseconds, number of launches and number of points processed, then resets the log. */
 void nmb_profile_enable(int on);
 int nmb_profile_collect(double* ms, int64_t* launches, int64_t* units, int n_classes);

@@ -115,7 +115,7 @@ def launch_count() -> int:
     return int(lib().nmb_launch_count())
 
 
-PROFILE_CLASSES = ("knn", "bound_scan", "geo", "geo_jvp", "color", "sampler")
+PROFILE_CLASSES = ("knn", "bound_scan", "geo", "geo_jvp", "color", "sampler", "knn_list")
 
 
 def profile_enable(on: bool):

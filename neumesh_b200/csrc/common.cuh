@@ -63,7 +63,7 @@ int sm_count();
 
 // Optional per-kernel-class device timing (bench.py's roofline): CUDA events recorded on the launching stream
 // around the launches of one class.  Disabled by default (no events, no overhead).
-enum ProfTag { PROF_KNN = 0, PROF_BOUND = 1, PROF_GEO = 2, PROF_GEO_JVP = 3, PROF_COLOR = 4, PROF_SAMPLER = 5, PROF_N = 6 };
+enum ProfTag { PROF_KNN = 0, PROF_BOUND = 1, PROF_GEO = 2, PROF_GEO_JVP = 3, PROF_COLOR = 4, PROF_SAMPLER = 5, PROF_KNN_LIST = 6, PROF_N = 7 };
 bool prof_enabled();
 void prof_begin(int tag, int64_t units, cudaStream_t stream);
 void prof_end(int tag, cudaStream_t stream);

@@ -737,7 +737,7 @@ knn_lists_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pt
 int launch_knn_lists(const nmb_grid* g, const float4* indicator_sorted, float w1, const float* xyz, const int32_t* off,
                      const int32_t* cnt, int64_t R, int64_t M, KnnOut out, cudaStream_t stream) {
   if (M <= 0 || R <= 0) return 0;
-  ProfScope prof(PROF_KNN, M, stream);
+  ProfScope prof(PROF_KNN_LIST, M, stream);
   knn_lists_kernel<<<(unsigned)ceil_div(R, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, xyz, off,
                                                                   cnt, R, out);
   NMB_LAUNCH_OK();
