@@ -209,9 +209,10 @@ def main():
     model.load_state_dict(sd)
     model = model.to(dev).eval()
     n_rays = H * W
-    lo, hi = parallel.shard_range(n_rays, rank, world)
-    host = [(o.pin_memory(), d.pin_memory()) for o, d in frames]
-    resident = [(o[lo:hi].to(dev), d[lo:hi].to(dev)) for o, d in frames]
+    sl = parallel.shard_slice(rank, world)           # interleaved: every rank gets the same hit / miss mix
+    n_mine = parallel.shard_count(n_rays, rank, world)
+    host = [(o[sl].contiguous().pin_memory(), d[sl].contiguous().pin_memory()) for o, d in frames]
+    resident = [(o.to(dev), d.to(dev)) for o, d in host]
     chunk = args.chunk or None
 
     def step_resident(i, skip=None):
@@ -273,8 +274,8 @@ def main():
 
         def step_e2e(i):
             o_h, d_h = host[i % len(host)]
-            o = o_h[lo:hi].to(dev, non_blocking=True)
-            d = d_h[lo:hi].to(dev, non_blocking=True)
+            o = o_h.to(dev, non_blocking=True)
+            d = d_h.to(dev, non_blocking=True)
             if world == 1 and not args.all_samples:
                 rgb, depth, _ = nb.volume_render(o, d, model, detailed_output=False, **RENDER_KW)
             else:
@@ -392,14 +393,14 @@ def main():
             cpu = {"value": rate, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
                    "sample": f"{args.cpu_rays} rays strided over frame 0 ({secs:.1f} s; oracle port of the reference "
                              f"renderer: torch CPU fp32 + scipy cKDTree exact KNN; os.cpu_count()={os.cpu_count()})"}
-        bo = (hi - lo) * 24
+        bo = n_mine * 24
         bi = n_rays * 16
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
             "dtype": "fp32 (MLPs: 3xTF32 tcgen05, fp32 accumulate)" if args.engine == "tcgen05" else "fp32",
-            "data": "synthetic", "config": {**workload_config(n_rays), "parallelism": f"ray-shard x{world} + all_gather",
+            "data": "synthetic", "config": {**workload_config(n_rays), "parallelism": f"interleaved ray-shard x{world} + all_gather",
                                             "mlp_engine": args.engine,
                                             "skip_dead_samples": not args.all_samples},
             "e2e": {"value": e2e_val, "unit": "rays/s", "ms_per_step": ms_e2e / args.steps,

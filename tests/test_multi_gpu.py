@@ -34,12 +34,13 @@ def _worker(rank, world, port, n_rays, q):
     from neumesh_b200 import parallel
     g = torch.Generator().manual_seed(0)
     o, d = torch.randn(n_rays, 3, generator=g), torch.randn(n_rays, 3, generator=g)
-    lo, hi = parallel.shard_range(n_rays, rank, world)
-    part = _fake_render(o[lo:hi], d[lo:hi])
+    sl = parallel.shard_slice(rank, world)
+    part = _fake_render(o[sl], d[sl])
+    assert part["rgb"].shape[0] == parallel.shard_count(n_rays, rank, world)
     full = parallel.gather_image(part, n_rays, rank, world)
     ref = _fake_render(o, d)
     ok = all(torch.equal(full[k], ref[k]) for k in ref)
-    q.put((rank, ok, lo, hi))
+    q.put((rank, ok, parallel.shard_count(n_rays, rank, world), 0))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -57,7 +58,18 @@ def test_ray_sharding_all_gather_gloo(n_rays):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok, _, _ in res)
-    assert res[0][2] == 0 and res[0][3] == res[1][2] and res[1][3] == n_rays  # contiguous cover
+    assert res[0][2] + res[1][2] == n_rays  # the interleaved slices cover every ray exactly once
+
+
+def test_interleaved_shards_cover_all_rays():
+    from neumesh_b200 import parallel
+    for n in (0, 1, 7, 1001):
+        for w in (1, 2, 4, 8):
+            idx = torch.arange(n)
+            parts = [idx[parallel.shard_slice(r, w)] for r in range(w)]
+            assert [len(p) for p in parts] == [parallel.shard_count(n, r, w) for r in range(w)]
+            assert torch.equal(torch.sort(torch.cat(parts))[0], idx)
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
 
 
 def test_shard_range_partitions():
