@@ -179,6 +179,9 @@ def main():
     ap.add_argument("--chunk", type=int, default=0, help="rays per kernel chunk (0 = library default)")
     ap.add_argument("--ref-rays", type=int, default=1024, help="rays per step of the CPU reference arm")
     ap.add_argument("--cpu-rays", type=int, default=1536, help="rays of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--simulate-world", type=int, default=1,
+                    help="(diagnostic, 1 GPU) render only rank 0's block-cyclic share of an N-way split and print the "
+                         "per-rank time: predicts N-GPU throughput without N GPUs; not a bench value")
     ap.add_argument("--all-samples", action="store_true",
                     help="evaluate colour / nabla at every sample like the reference does, instead of only where the "
                          "visibility weight is non-zero (bit-identical outputs either way)")
@@ -209,8 +212,9 @@ def main():
     model.load_state_dict(sd)
     model = model.to(dev).eval()
     n_rays = H * W
-    sl = parallel.shard_slice(rank, world)           # interleaved: every rank gets the same hit / miss mix
-    n_mine = parallel.shard_count(n_rays, rank, world)
+    sim = max(1, args.simulate_world)                # single-GPU what-if: render only rank 0's share of a `sim`-way split
+    sl = parallel.shard_indices(n_rays, rank, world * sim)   # block-cyclic: every rank gets the same hit / miss mix
+    n_mine = parallel.shard_count(n_rays, rank, world * sim)
     host = [(o[sl].contiguous().pin_memory(), d[sl].contiguous().pin_memory()) for o, d in frames]
     resident = [(o.to(dev), d.to(dev)) for o, d in host]
     chunk = args.chunk or None
@@ -219,7 +223,30 @@ def main():
         o, d = resident[i % len(resident)]
         part = render_fused(o, d, model, chunk=chunk, skip_dead_samples=(not args.all_samples) if skip is None else skip,
                             **RENDER_KW)
+        if sim > 1:
+            return part
         return parallel.gather_image(part, n_rays, rank, world)
+
+    if sim > 1:
+        assert world == 1, "--simulate-world is a single-GPU diagnostic"
+        with torch.no_grad():
+            for i in range(args.warmup):
+                step_resident(i)
+            torch.cuda.synchronize()
+            _lib.profile_enable(True)
+            _lib.profile_collect()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(args.steps):
+                step_resident(args.warmup + i)
+            e1.record()
+            torch.cuda.synchronize()
+            prof = _lib.profile_collect()
+        ms = e0.elapsed_time(e1) / args.steps
+        print(json.dumps({"diagnostic": "simulate_world", "world": sim, "rays_rank0": n_mine, "ms_per_step_rank0": ms,
+                          "predicted_rays_per_s": n_rays / (ms * 1e-3),
+                          "kernels_ms": {k: v["ms"] / args.steps for k, v in prof.items() if v["launches"]}}), flush=True)
+        return
 
     def barrier():
         if world > 1:

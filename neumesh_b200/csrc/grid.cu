@@ -16,6 +16,7 @@
 #include <cub/cub.cuh>
 #include <math_constants.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "grid.cuh"
@@ -661,20 +662,25 @@ knn_distance_kernel(const float4* __restrict__ nodes, const float4* __restrict__
 // a few percent of the final one and the octree walk prunes almost everything).  A warp = 32 neighbouring rays.
 __global__ void __launch_bounds__(128)
 knn_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts, const float4* __restrict__ indicator,
-                float w1, PointSrc src, int S, KnnOut out) {
-  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (r >= src.R) return;
+                float w1, PointSrc src, int S, int seg, KnnOut out) {
+  // thread t handles samples [g * seg, (g + 1) * seg) of ray r, t = g * R + r: with few rays (multi-GPU shards) a
+  // ray's samples are split over several threads so that the launch still fills the GPU (one cold walk per segment)
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t r = t % src.R;
+  const int s_begin = (int)(t / src.R) * seg;
+  if (s_begin >= S) return;
+  const int s_end = min(s_begin + seg, S);
   const float ox = src.rays_o[r * 3 + 0], oy = src.rays_o[r * 3 + 1], oz = src.rays_o[r * 3 + 2];
   const float dx = src.rays_d[r * 3 + 0], dy = src.rays_d[r * 3 + 1], dz = src.rays_d[r * 3 + 2];
   float d2[KNN_K];
   int32_t ix[KNN_K];
-  for (int s = 0; s < S; ++s) {
+  for (int s = s_begin; s < s_end; ++s) {
     const int64_t p = (int64_t)s * src.R + r;
     const float z = src.z[p];
     const float qx = __fadd_rn(ox, __fmul_rn(z, dx));
     const float qy = __fadd_rn(oy, __fmul_rn(z, dy));
     const float qz = __fadd_rn(oz, __fmul_rn(z, dz));
-    if (s == 0) {
+    if (s == s_begin) {
       knn_walk<KNN_K, false>(nodes, pts, qx, qy, qz, d2, ix);
     } else {
       warm_rerank<KNN_K>(pts, qx, qy, qz, d2, ix);
@@ -751,8 +757,14 @@ int launch_knn_distance(const nmb_grid* g, const float4* indicator_sorted, float
   if (P <= 0) return 0;
   ProfScope prof(PROF_KNN, P, stream);
   if (!src.xyz && src.R >= RAY_KERNEL_MIN_RAYS && P % src.R == 0) {
-    knn_rays_kernel<<<(unsigned)ceil_div(src.R, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src,
-                                                                       (int)(P / src.R), out);
+    const int S = (int)(P / src.R);
+    // segments per ray: enough threads to fill the GPU (~2 waves of 1024 threads per SM), at least 8 samples each
+    int64_t nseg = ceil_div((int64_t)sm_count() * 2048 * 2, src.R);
+    nseg = std::max<int64_t>(1, std::min<int64_t>(nseg, ceil_div(S, 8)));
+    const int seg = (int)ceil_div(S, nseg);
+    nseg = ceil_div(S, seg);
+    knn_rays_kernel<<<(unsigned)ceil_div(src.R * nseg, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1,
+                                                                              src, S, seg, out);
     NMB_LAUNCH_OK();
     return 0;
   }
@@ -798,9 +810,14 @@ bound_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ p
                   const float4* __restrict__ indicator, float w1, const float* __restrict__ rays_o,
                   const float* __restrict__ dirs, const float* __restrict__ near, const float* __restrict__ far,
                   int64_t R, int n_grid, float thresh, int32_t* __restrict__ bnear, int32_t* __restrict__ bfar,
-                  ShellGrid shell) {
-  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (r >= R) return;
+                  ShellGrid shell, int two_sided) {
+  // two_sided = 0: one thread scans front then back.  two_sided = 1 (few rays): thread r scans from the front,
+  // thread R + r from the back; a ray has a hit from the front iff it has one from the back, so both extrema are set
+  // (or neither) exactly as in the one-thread version.
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= R * (two_sided ? 2 : 1)) return;
+  const int64_t r = t % R;
+  const int side = (int)(t / R);
   const float ox = rays_o[r * 3 + 0], oy = rays_o[r * 3 + 1], oz = rays_o[r * 3 + 2];
   const float dx = dirs[r * 3 + 0], dy = dirs[r * 3 + 1], dz = dirs[r * 3 + 2];
   const float nr = near[r], fr = far[r];
@@ -839,14 +856,25 @@ bound_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ p
   };
   int first = -1;
   float depth = 0.f;
-  for (int s = 0; s < n_grid; ++s) {
-    if (ds_at(s, depth) < thresh) {
-      first = s;
-      bnear[r] = __float_as_int(depth);
-      break;
+  if (side == 0) {
+    for (int s = 0; s < n_grid; ++s) {
+      if (ds_at(s, depth) < thresh) {
+        first = s;
+        bnear[r] = __float_as_int(depth);
+        break;
+      }
     }
+    if (first < 0 || two_sided) return;  // no sample inside the shell: bnear / bfar keep their "unset" values
+  } else {
+    first = -1;   // back-scanning thread: stops at its own first hit (exists iff the front scan finds one)
+    for (int s = n_grid - 1; s >= 0; --s) {
+      if (ds_at(s, depth) < thresh) {
+        bfar[r] = __float_as_int(depth);
+        break;
+      }
+    }
+    return;
   }
-  if (first < 0) return;  // no sample inside the shell: bnear / bfar keep their "unset" values
   for (int s = n_grid - 1; s >= first; --s) {
     // s == first is known to be a hit: the loop always terminates with bfar set
     if (s == first || ds_at(s, depth) < thresh) {
@@ -867,9 +895,10 @@ int launch_bound_scan(const nmb_grid* g, const float4* indicator, float w1, cons
   if (n <= 0) return 0;
   ProfScope prof(PROF_BOUND, n, stream);
   if (R >= RAY_KERNEL_MIN_RAYS) {
-    bound_rays_kernel<<<(unsigned)ceil_div(R, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator, w1, rays_o, dirs,
-                                                                     near, far, R, n_grid, thresh, bnear, bfar,
-                                                                     (thresh == 0.1f) ? shell : ShellGrid{});
+    const int two_sided = (R < (int64_t)sm_count() * 2048) ? 1 : 0;
+    bound_rays_kernel<<<(unsigned)ceil_div(R * (two_sided ? 2 : 1), 128), 128, 0, stream>>>(
+        g->nodes.p, g->pts.p, indicator, w1, rays_o, dirs, near, far, R, n_grid, thresh, bnear, bfar,
+        (thresh == 0.1f) ? shell : ShellGrid{}, two_sided);
     NMB_LAUNCH_OK();
     return 0;
   }

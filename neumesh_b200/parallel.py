@@ -2,7 +2,7 @@
 
 The reference's strategy is ``nn.DataParallel`` over rays (``models/trainer.py:39-42``: scatter rays, replicate the
 module, gather on device 0).  Here: one process per GPU; every rank holds the full mesh / vertex tables / MLPs
-(read-only at inference), renders an interleaved slice of the ray range and contributes it to ONE
+(read-only at inference), renders a block-cyclic slice of the ray range and contributes it to ONE
 ``all_gather_into_tensor`` of the packed ``[rays, C]`` output tile (C = 5, or 8 with normals) over NCCL/NVLink.
 There is no data-path collective besides that gather (rays are independent).
 """
@@ -24,25 +24,34 @@ def shard_range(n_rays: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def shard_slice(rank: int, world: int) -> slice:
-    """Interleaved partition: rank r renders rays r, r + world, r + 2 world, ...  Per-ray cost is very uneven (rays
-    that hit the object have ~75 live samples, rays that miss have none), so contiguous image bands would leave the
-    ranks holding the object's band as stragglers; an interleaved split gives every rank the same mix.  Spatial
-    coherence inside a rank is restored by the library's Morton ordering of its rays."""
-    return slice(rank, None, world)
+SHARD_BLOCK = 128  # rays per block of the block-cyclic distribution
 
 
-def shard_count(n_rays: int, rank: int, world: int) -> int:
-    return (n_rays - rank + world - 1) // world if n_rays > rank else 0
+def shard_indices(n_rays: int, rank: int, world: int, block: int = SHARD_BLOCK, device=None) -> torch.Tensor:
+    """Block-cyclic partition: blocks of ``block`` consecutive rays are dealt round-robin to the ranks.
+
+    Per-ray cost is very uneven (rays that hit the object have ~75 live samples, rays that miss have none), so
+    contiguous image bands would leave the ranks that hold the object's band as stragglers, while a ray-by-ray
+    interleave would destroy the locality the octree walk relies on.  Blocks of 128 consecutive rays keep neighbouring
+    pixels together and still give every rank the same mix; inside a rank the library re-orders its rays along a
+    Morton curve anyway."""
+    idx = torch.arange(n_rays, device=device)
+    return idx[(idx // block) % world == rank]
+
+
+def shard_count(n_rays: int, rank: int, world: int, block: int = SHARD_BLOCK) -> int:
+    full, rem = divmod(n_rays, block * world)
+    return full * block + min(max(rem - rank * block, 0), block)
 
 
 def gather_image(part: dict, n_rays: int, rank: int, world: int) -> "OrderedDict[str, torch.Tensor]":
-    """part: this rank's outputs for its ``shard_slice`` -> full-image outputs (caller order) on every rank, through
+    """part: this rank's outputs for its ``shard_indices`` -> full-image outputs (caller order) on every rank, through
     ONE ``all_gather_into_tensor`` of the packed ``[rays, C]`` tile."""
     keys = [(k, c) for k, c in PACK_KEYS if k in part]
     width = sum(c for _, c in keys)
-    per = -(-n_rays // world)  # ceil: equal-size slots so a single all_gather_into_tensor suffices
-    mine = shard_count(n_rays, rank, world)
+    counts = [shard_count(n_rays, r, world) for r in range(world)]
+    per = max(max(counts), 1)  # equal-size slots so a single all_gather_into_tensor suffices
+    mine = counts[rank]
     ref = part[keys[0][0]]
     tile = torch.zeros(per, width, dtype=torch.float32, device=ref.device)
     col = 0
@@ -50,12 +59,13 @@ def gather_image(part: dict, n_rays: int, rank: int, world: int) -> "OrderedDict
         tile[:mine, col:col + c] = part[k].reshape(mine, c)
         col += c
     if world == 1:
-        full = tile[None]
+        flat = tile[:n_rays]
     else:
         full = torch.empty(world, per, width, dtype=torch.float32, device=ref.device)
         dist.all_gather_into_tensor(full.view(world * per, width), tile)
-    # element (rank r, slot i) is ray i * world + r: transpose, flatten, drop the padding at the end
-    flat = full.transpose(0, 1).reshape(world * per, width)[:n_rays]
+        flat = torch.empty(n_rays, width, dtype=torch.float32, device=ref.device)
+        for r in range(world):
+            flat[shard_indices(n_rays, r, world, device=ref.device)] = full[r, :counts[r]]
     out = OrderedDict()
     col = 0
     for k, c in keys:
@@ -71,7 +81,7 @@ def render_sharded(rays_o, rays_d, model, **render_kwargs):
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     n = rays_o.reshape(-1, 3).shape[0]
-    sl = shard_slice(rank, world)
+    sl = shard_indices(n, rank, world, device=rays_o.device)
     part = render_fused(rays_o.reshape(-1, 3)[sl].contiguous(), rays_d.reshape(-1, 3)[sl].contiguous(), model,
                         **render_kwargs)
     return gather_image(part, n, rank, world)

@@ -34,7 +34,7 @@ def _worker(rank, world, port, n_rays, q):
     from neumesh_b200 import parallel
     g = torch.Generator().manual_seed(0)
     o, d = torch.randn(n_rays, 3, generator=g), torch.randn(n_rays, 3, generator=g)
-    sl = parallel.shard_slice(rank, world)
+    sl = parallel.shard_indices(n_rays, rank, world)
     part = _fake_render(o[sl], d[sl])
     assert part["rgb"].shape[0] == parallel.shard_count(n_rays, rank, world)
     full = parallel.gather_image(part, n_rays, rank, world)
@@ -45,7 +45,7 @@ def _worker(rank, world, port, n_rays, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_rays", [1000, 1001, 3])
+@pytest.mark.parametrize("n_rays", [1000, 1001, 3, 300])
 def test_ray_sharding_all_gather_gloo(n_rays):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -58,18 +58,18 @@ def test_ray_sharding_all_gather_gloo(n_rays):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok, _, _ in res)
-    assert res[0][2] + res[1][2] == n_rays  # the interleaved slices cover every ray exactly once
+    assert res[0][2] + res[1][2] == n_rays  # the block-cyclic slices cover every ray exactly once
 
 
-def test_interleaved_shards_cover_all_rays():
+def test_block_cyclic_shards_cover_all_rays():
     from neumesh_b200 import parallel
-    for n in (0, 1, 7, 1001):
+    for n in (0, 1, 7, 1001, 640000):
         for w in (1, 2, 4, 8):
             idx = torch.arange(n)
-            parts = [idx[parallel.shard_slice(r, w)] for r in range(w)]
+            parts = [parallel.shard_indices(n, r, w) for r in range(w)]
             assert [len(p) for p in parts] == [parallel.shard_count(n, r, w) for r in range(w)]
             assert torch.equal(torch.sort(torch.cat(parts))[0], idx)
-            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= parallel.SHARD_BLOCK
 
 
 def test_shard_range_partitions():
