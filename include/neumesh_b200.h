@@ -106,7 +106,8 @@ int nmb_field_forward(const nmb_field* f, const float* xyz, const float* view_di
 
 /* Shell-free certificate grid used by nmb_render's bounded near/far scan (csrc/shell.cu): builds it if necessary and
  * copies the G^3 bytes to `cells` (device, may be NULL to query the size only).  cells[(z*G + y)*G + x] == 1 means:
- * every point of that cell of the grid over [-B, B]^3 provably has mesh distance ds >= 0.1.  Returns G and B. */
+ * every point of that cell of the grid over [-B, B]^3 provably has mesh distance ds >= 0.1; == 2: every point provably
+ * has ds < 0.1; == 0: not proven either way.  Returns G and B. */
 int nmb_field_shell_grid(const nmb_field* f, uint8_t* cells, int32_t* G, float* B, void* stream);
 
 /* ---- renderer ------------------------------------------------------------------------------------------------

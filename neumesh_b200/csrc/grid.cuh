@@ -50,8 +50,9 @@ __device__ __forceinline__ float linspace01(int i, int n) {
   return (i < n / 2) ? __fmul_rn(step, (float)i) : fmaf(-step, (float)(n - 1 - i), 1.0f);
 }
 
-// "Shell-free" certificate grid (csrc/shell.cu): cell (i,j,k) of a G^3 grid over [-B,B]^3 is 1 when EVERY point of the
-// cell provably has mesh distance ds >= 0.1 + margin, so the bounded-near/far scan may skip it without evaluating.
+// Shell certificate grid (csrc/shell.cu) over [-B,B]^3: cell value 1 = EVERY point of the cell provably has mesh distance
+// ds >= 0.1 (the bounded-near/far scan skips it), 2 = every point provably has ds < 0.1 (a hit without evaluation),
+// 0 = not proven either way (evaluated exactly).
 struct ShellGrid {
   const uint8_t* cells = nullptr;   // nullptr = no certificate available
   int G = 0;

@@ -20,12 +20,14 @@
 #include <cmath>
 
 #include "field.cuh"
+#include "knn_walk.cuh"
 
 namespace nmb {
 
 constexpr int SHELL_G = 128;
 constexpr float SHELL_B = 1.001f;          // grid covers [-B, B]^3 (the unit bounding sphere of the reference's scenes)
 constexpr float SHELL_THR = 0.1f + 2e-3f;  // certificate threshold: renderer.py:73 distance_thresh + rounding margin
+constexpr float SHELL_THR_IN = 0.1f - 2e-3f;  // "inside" certificate: every point of the cell has ds < 0.1
 
 // per-node indicator statistics, bottom-up: {mean vector, max deviation of any vertex below the node from it}
 __global__ void node_normals_kernel(int32_t first, int32_t count, const float4* __restrict__ nodes,
@@ -66,6 +68,59 @@ __global__ void node_normals_kernel(int32_t first, int32_t count, const float4* 
 __device__ __forceinline__ float f_lower(float w1, float nv_lo, float rlo, float rhi) {
   const float num = w1 * nv_lo + rlo * rlo * rlo;
   return num >= 0.f ? num / (w1 + rhi) : num / (w1 + rlo);
+}
+__device__ __forceinline__ float f_upper(float w1, float nv_hi, float rlo, float rhi) {
+  const float num = w1 * nv_hi + rhi * rhi * rhi;
+  return num >= 0.f ? num / (w1 + rlo) : num / (w1 + rhi);
+}
+
+// "Inside" certificate: ds(x) <= max_k f(x - p_k, n_k) over the 8 nearest vertices of x, and for x in the cell those
+// lie within R_S = d8(c) + 2 delta of the centre c (d8 = distance to the 8th neighbour of c, from an exact walk).
+// If f is bounded below the threshold for EVERY vertex inside that ball, every point of the cell is inside the shell.
+__device__ bool certify_inside(const float4* __restrict__ nodes, const float4* __restrict__ pts,
+                               const float4* __restrict__ indicator, const float4* __restrict__ stats, float w1,
+                               float cx, float cy, float cz, float delta) {
+  float d2[KNN_K];
+  int32_t ix[KNN_K];
+  knn_walk<KNN_K, false>(nodes, pts, cx, cy, cz, d2, ix);
+  const float RS = sqrtf(d2[KNN_K - 1]) * 1.00001f + 2.f * delta + 1e-6f;
+  int32_t stack[STACK_MAX];
+  int sp = 1;
+  stack[0] = 0;
+  while (sp > 0) {
+    const int32_t n = stack[--sp];
+    const float4 cr = __ldg(&nodes[NODE_F4 * n + 2]);
+    const float ex = cx - cr.x, ey = cy - cr.y, ez = cz - cr.z;
+    const float D = sqrtf(ex * ex + ey * ey + ez * ez);
+    if (D * 0.99999f - cr.w > RS) continue;                       // no vertex of the node can be a neighbour
+    const float rlo = fmaxf(D * 0.99999f - cr.w - delta, 0.f);
+    const float rhi = D * 1.00001f + cr.w + delta;
+    const float4 st = __ldg(&stats[n]);
+    const float nbn = sqrtf(st.x * st.x + st.y * st.y + st.z * st.z);
+    const float nv_hi = (st.x * ex + st.y * ey + st.z * ez) + nbn * (cr.w + delta) + st.w * rhi + 1e-6f;
+    if (f_upper(w1, nv_hi, rlo, rhi) < SHELL_THR_IN) continue;    // whole node bounded
+    const int32_t link = __float_as_int(__ldg(&nodes[NODE_F4 * n]).w);
+    const int32_t cnt = __float_as_int(__ldg(&nodes[NODE_F4 * n + 1]).w);
+    if (cnt < 0) {
+      for (int32_t i = link; i < link - cnt; ++i) {
+        const float4 p = __ldg(&pts[i]);
+        const float vx = cx - p.x, vy = cy - p.y, vz = cz - p.z;
+        const float rc = sqrtf(vx * vx + vy * vy + vz * vz);
+        if (rc * 0.99999f > RS) continue;
+        const float4 nv = __ldg(&indicator[i]);
+        const float plo = fmaxf(rc * 0.99999f - delta, 0.f), phi = rc * 1.00001f + delta;
+        const float nn = sqrtf(nv.x * nv.x + nv.y * nv.y + nv.z * nv.z);
+        const float hi = (nv.x * vx + nv.y * vy + nv.z * vz) + nn * delta + 1e-6f;
+        if (!(f_upper(w1, hi, plo, phi) < SHELL_THR_IN)) return false;
+      }
+    } else {
+      for (int32_t c = 0; c < cnt; ++c) {
+        if (sp >= STACK_MAX) return false;
+        stack[sp++] = link + c;
+      }
+    }
+  }
+  return true;
 }
 
 __global__ void __launch_bounds__(128)
@@ -116,7 +171,9 @@ shell_certify_kernel(const float4* __restrict__ nodes, const float4* __restrict_
       if (sp >= STACK_MAX) ok = false;   // cannot happen (7 * depth + 8 < STACK_MAX); stay conservative
     }
   }
-  cells[cell] = ok ? 1 : 0;
+  uint8_t code = ok ? 1 : 0;
+  if (!ok && certify_inside(nodes, pts, indicator, stats, w1, cx, cy, cz, delta)) code = 2;
+  cells[cell] = code;   // 1: every point has ds >= 0.1; 2: every point has ds < 0.1; 0: not proven either way
 }
 
 int ensure_shell_grid(const nmb_field* f, cudaStream_t stream) {

@@ -482,21 +482,25 @@ def test_shell_certificate_is_sound(learn_w):
     cells, B = model.shell_free_grid()
     G = cells.shape[0]
     assert G > 1
-    frac = cells.float().mean().item()
+    frac = (cells == 1).float().mean().item()
+    frac_in = (cells == 2).float().mean().item()
     g = torch.Generator(device="cpu").manual_seed(0)
     x = ((torch.rand(3_000_000, 3, generator=g) * 2 - 1) * B * 0.9999).to(dev)
     ijk = ((x + B) * (0.5 * G / B)).long().clamp_(0, G - 1)
-    marked = cells[ijk[:, 2], ijk[:, 1], ijk[:, 0]].bool()
+    code = cells[ijk[:, 2], ijk[:, 1], ijk[:, 0]]
+    marked, inside = code == 1, code == 2
     with torch.no_grad():
         ds, _, _ = model.compute_distance(x[marked])
-    print(f"certified cells {frac:.3f}; sampled points in certified cells {int(marked.sum())}; "
-          f"min ds among them {ds.min().item():.4f}")
+        ds_in, _, _ = model.compute_distance(x[inside])
+    print(f"cells proven outside {frac:.3f} / inside {frac_in:.3f}; sampled points: outside {int(marked.sum())} "
+          f"(min ds {ds.min().item():.4f}), inside {int(inside.sum())} (max ds {ds_in.max().item():.4f})")
     assert marked.float().mean() > 0.2, "certificate should cover a sizeable part of the volume"
     assert ds.min().item() >= 0.1
+    assert inside.sum() > 1000 and ds_in.max().item() < 0.1
     # and it is not vacuous: cells near the surface are left unmarked
     near = torch.from_numpy(mesh.vertices[:2000]).float().to(dev)
     ijk = ((near + B) * (0.5 * G / B)).long().clamp_(0, G - 1)
-    assert not cells[ijk[:, 2], ijk[:, 1], ijk[:, 0]].any()
+    assert not (cells[ijk[:, 2], ijk[:, 1], ijk[:, 0]] == 1).any()
 
 
 def test_get_rays_matches_synth():
