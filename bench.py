@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--simulate-world", type=int, default=1,
                     help="(diagnostic, 1 GPU) render only rank 0's block-cyclic share of an N-way split and print the "
                          "per-rank time: predicts N-GPU throughput without N GPUs; not a bench value")
+    ap.add_argument("--tune", action="store_true", help="(diagnostic) with --simulate-world 1: print per-class times only")
     ap.add_argument("--all-samples", action="store_true",
                     help="evaluate colour / nabla at every sample like the reference does, instead of only where the "
                          "visibility weight is non-zero (bit-identical outputs either way)")
@@ -227,7 +228,7 @@ def main():
             return part
         return parallel.gather_image(part, n_rays, rank, world)
 
-    if sim > 1:
+    if sim > 1 or args.tune:
         assert world == 1, "--simulate-world is a single-GPU diagnostic"
         with torch.no_grad():
             for i in range(args.warmup):

@@ -160,6 +160,17 @@ int nmb_upsample_step(const float* z, const float* sdf, int64_t N, int32_t n, in
 int nmb_get_rays(const float* c2w_host /*HOST 12 floats*/, const float* intr_host /*HOST 5 floats*/, int32_t H,
                  int32_t W, float* rays_o, float* rays_d, void* stream);
 
+/* Image packing (render.py:219-241: clip to [0,1], scale to 255, RGB -> BGR as cv2.imwrite expects): rgb [N,3] fp32
+ * -> bgr8 [N,3] uint8 (values truncated like numpy's astype(np.uint8) after the reference's `* 255`). */
+int nmb_pack_bgr8(const float* rgb, int64_t N, uint8_t* bgr8, void* stream);
+
+/* Area-weighted vertex normals (what Open3D's compute_vertex_normals gives MeshGrid at models/mesh_grid.py:20): sum of
+ * the un-normalised face normals (cross products) of the incident triangles, normalised.  vertices [V,3] fp32,
+ * triangles [T,3] int32, normals [V,3] fp32 (output).  Used when an editing tool deforms the mesh and the grid /
+ * normals must be rebuilt (editing/render_geometry_editing.py:37-67). */
+int nmb_vertex_normals(const float* vertices, int64_t V, const int32_t* triangles, int64_t T, float* normals,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "grid.cuh"
@@ -130,13 +131,13 @@ __global__ void lvl_create_kernel(const uint32_t* __restrict__ code, const int32
 }
 
 __global__ void lvl_activate_kernel(const int32_t* __restrict__ newnode, const int32_t* __restrict__ nbegin,
-                                    const int32_t* __restrict__ nend, int64_t V, int can_split,
+                                    const int32_t* __restrict__ nend, int64_t V, int can_split, int leaf_max,
                                     int32_t* __restrict__ pnode) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= V) return;
   int32_t g = newnode[i];
   int32_t r = -1;
-  if (g >= 0 && can_split && (nend[g] - nbegin[g]) > LEAF_MAX) r = g;
+  if (g >= 0 && can_split && (nend[g] - nbegin[g]) > leaf_max) r = g;
   pnode[i] = r;
 }
 
@@ -307,7 +308,9 @@ static int build_grid(const float* vertices, int64_t V, cudaStream_t stream, nmb
   NMB_LAUNCH_OK();
 
   // level-by-level subdivision
-  const int64_t cap = V + (int64_t)(L + 1) * (V / (LEAF_MAX + 1) + 1) + 16;
+  // leaf capacity (points per leaf): tunable for experiments, default LEAF_MAX
+  const int leaf_max = getenv("NMB_LEAF_MAX") ? std::max(1, atoi(getenv("NMB_LEAF_MAX"))) : LEAF_MAX;
+  const int64_t cap = V + (int64_t)(L + 1) * (V / (leaf_max + 1) + 1) + 16;
   DevBuf<int32_t> nbegin, nend, nfirst, nlast, pnode, newnode, head, cid;
   NMB_CUDA_OK(nbegin.alloc(cap));
   NMB_CUDA_OK(nend.alloc(cap));
@@ -331,7 +334,7 @@ static int build_grid(const float* vertices, int64_t V, cudaStream_t stream, nmb
     NMB_CUDA_OK(cudaMemcpyAsync(nfirst.p, &root[2], 4, cudaMemcpyHostToDevice, stream));
     NMB_CUDA_OK(cudaMemcpyAsync(nlast.p, &root[3], 4, cudaMemcpyHostToDevice, stream));
     // all points start in the root (V >= 8 > ... root splits iff V > LEAF_MAX and L > 0)
-    int fill = (V > LEAF_MAX && L > 0) ? 0 : -1;
+    int fill = (V > leaf_max && L > 0) ? 0 : -1;
     NMB_CUDA_OK(cudaMemsetAsync(pnode.p, fill == 0 ? 0 : 0xff, sizeof(int32_t) * V, stream));
   }
   int32_t n_nodes = 1;
@@ -353,7 +356,7 @@ static int build_grid(const float* vertices, int64_t V, cudaStream_t stream, nmb
                                                                  nbegin.p, nend.p, nfirst.p, nlast.p, newnode.p);
     NMB_LAUNCH_OK();
     lvl_activate_kernel<<<(unsigned)blocks, threads, 0, stream>>>(newnode.p, nbegin.p, nend.p, V, (l + 1 < L) ? 1 : 0,
-                                                                   pnode.p);
+                                                                   leaf_max, pnode.p);
     NMB_LAUNCH_OK();
     n_nodes += n_new;
     lvl_off.push_back(n_nodes);
@@ -451,7 +454,8 @@ knn_distance_kernel(const float4* __restrict__ nodes, const float4* __restrict__
 // Ray-ordered variant: one thread per RAY walks its S samples in depth order and warm-starts every query with the
 // previous sample's neighbours (consecutive samples are <~0.03 apart, so the initial 8th-best bound is already within
 // a few percent of the final one and the octree walk prunes almost everything).  A warp = 32 neighbouring rays.
-__global__ void __launch_bounds__(128)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 knn_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts, const float4* __restrict__ indicator,
                 float w1, PointSrc src, int S, int seg, KnnOut out) {
   // thread t handles samples [g * seg, (g + 1) * seg) of ray r, t = g * R + r: with few rays (multi-GPU shards) a
@@ -554,8 +558,11 @@ int launch_knn_distance(const nmb_grid* g, const float4* indicator_sorted, float
     nseg = std::max<int64_t>(1, std::min<int64_t>(nseg, ceil_div(S, 8)));
     const int seg = (int)ceil_div(S, nseg);
     nseg = ceil_div(S, seg);
-    knn_rays_kernel<<<(unsigned)ceil_div(src.R * nseg, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1,
-                                                                              src, S, seg, out);
+    static const int minb = getenv("NMB_KNN_MINB") ? atoi(getenv("NMB_KNN_MINB")) : 10;
+    const unsigned gridn = (unsigned)ceil_div(src.R * nseg, 128);
+    if (minb >= 12) knn_rays_kernel<12><<<gridn, 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src, S, seg, out);
+    else if (minb >= 10) knn_rays_kernel<10><<<gridn, 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src, S, seg, out);
+    else knn_rays_kernel<8><<<gridn, 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src, S, seg, out);
     NMB_LAUNCH_OK();
     return 0;
   }

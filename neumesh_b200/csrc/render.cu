@@ -440,6 +440,45 @@ __global__ void get_rays_kernel(int H, int W, float fx, float fy, float cx, floa
   rays_o[i * 3 + 2] = tz;
 }
 
+__global__ void pack_bgr8_kernel(const float* __restrict__ rgb, int64_t N, uint8_t* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = fminf(fmaxf(rgb[i * 3 + c], 0.f), 1.f) * 255.f;
+    out[i * 3 + (2 - c)] = (uint8_t)v;
+  }
+}
+
+__global__ void face_normals_kernel(const float* __restrict__ v, const int32_t* __restrict__ tri, int64_t T,
+                                    float* __restrict__ acc) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const int32_t a = tri[t * 3], b = tri[t * 3 + 1], c = tri[t * 3 + 2];
+  const float ax = v[a * 3], ay = v[a * 3 + 1], az = v[a * 3 + 2];
+  const float ux = v[b * 3] - ax, uy = v[b * 3 + 1] - ay, uz = v[b * 3 + 2] - az;
+  const float wx = v[c * 3] - ax, wy = v[c * 3 + 1] - ay, wz = v[c * 3 + 2] - az;
+  const float nx = uy * wz - uz * wy, ny = uz * wx - ux * wz, nz = ux * wy - uy * wx;
+  const int32_t ids[3] = {a, b, c};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    atomicAdd(acc + (int64_t)ids[k] * 3 + 0, nx);
+    atomicAdd(acc + (int64_t)ids[k] * 3 + 1, ny);
+    atomicAdd(acc + (int64_t)ids[k] * 3 + 2, nz);
+  }
+}
+
+__global__ void normalize_rows_kernel(float* __restrict__ n, int64_t V) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= V) return;
+  const float x = n[i * 3], y = n[i * 3 + 1], z = n[i * 3 + 2];
+  float l = sqrtf(x * x + y * y + z * z);
+  if (l == 0.f) l = 1.f;
+  n[i * 3] = x / l;
+  n[i * 3 + 1] = y / l;
+  n[i * 3 + 2] = z / l;
+}
+
 }  // namespace nmb
 
 namespace {
@@ -721,6 +760,28 @@ int nmb_upsample_step(const float* z, const float* sdf, int64_t N, int32_t n, in
   if (N <= 0) return 0;
   nmb::upsample_kernel<<<(unsigned)nmb::ceil_div(N, nmb::RT), nmb::RT, 0, static_cast<cudaStream_t>(stream)>>>(
       N, n, n_new, inv_s, z, sdf, scratch, z_new);
+  NMB_LAUNCH_OK();
+  return 0;
+}
+
+int nmb_pack_bgr8(const float* rgb, int64_t N, uint8_t* bgr8, void* stream) {
+  NMB_CHECK(rgb && bgr8, "null argument");
+  if (N <= 0) return 0;
+  nmb::pack_bgr8_kernel<<<(unsigned)nmb::ceil_div(N, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rgb, N, bgr8);
+  NMB_LAUNCH_OK();
+  return 0;
+}
+
+int nmb_vertex_normals(const float* vertices, int64_t V, const int32_t* triangles, int64_t T, float* normals,
+                       void* stream_) {
+  NMB_CHECK(vertices && triangles && normals && V > 0, "bad argument");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  NMB_CUDA_OK(cudaMemsetAsync(normals, 0, sizeof(float) * 3 * V, stream));
+  if (T > 0) {
+    nmb::face_normals_kernel<<<(unsigned)nmb::ceil_div(T, 256), 256, 0, stream>>>(vertices, triangles, T, normals);
+    NMB_LAUNCH_OK();
+  }
+  nmb::normalize_rows_kernel<<<(unsigned)nmb::ceil_div(V, 256), 256, 0, stream>>>(normals, V);
   NMB_LAUNCH_OK();
   return 0;
 }

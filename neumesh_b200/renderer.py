@@ -361,3 +361,26 @@ def get_rays(c2w, intrinsics, H, W, device=None):
                                            intr.ctypes.data_as(C.POINTER(C.c_float)), H, W, _lib.ptr(o), _lib.ptr(d),
                                            _lib.stream_ptr(device)))
     return o, d
+
+
+def pack_bgr8(rgb, H=None, W=None):
+    """CUDA ``nmb_pack_bgr8``: rgb [N,3] float -> uint8 BGR (``[H,W,3]`` if H, W given), the conversion ``render.py``
+    does on the host before ``cv2.imwrite`` (render.py:219-241)."""
+    _lib.require_cuda(rgb, "pack_bgr8")
+    flat = rgb.detach().reshape(-1, 3).float().contiguous()
+    out = torch.empty(flat.shape[0], 3, dtype=torch.uint8, device=flat.device)
+    with torch.cuda.device(flat.device):
+        _lib.check(_lib.lib().nmb_pack_bgr8(_lib.ptr(flat), flat.shape[0], _lib.ptr(out), _lib.stream_ptr(flat.device)))
+    return out.reshape(H, W, 3) if H and W else out
+
+
+def vertex_normals(vertices, triangles):
+    """CUDA ``nmb_vertex_normals``: area-weighted vertex normals (Open3D ``compute_vertex_normals`` semantics)."""
+    _lib.require_cuda(vertices, "vertex_normals")
+    v = vertices.detach().float().contiguous()
+    t = triangles.detach().to(torch.int32).contiguous()
+    out = torch.empty_like(v)
+    with torch.cuda.device(v.device):
+        _lib.check(_lib.lib().nmb_vertex_normals(_lib.ptr(v), v.shape[0], _lib.ptr(t), t.shape[0], _lib.ptr(out),
+                                                 _lib.stream_ptr(v.device)))
+    return out

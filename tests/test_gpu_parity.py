@@ -512,3 +512,29 @@ def test_get_rays_matches_synth():
     o, d = get_rays(pose, K, H, W, device=dev)
     o_ref, d_ref = synth.pinhole_rays(pose, H, W, f, f, W / 2, H / 2)
     assert (o.cpu() - o_ref).abs().max() < 1e-6 and (d.cpu() - d_ref).abs().max() < 1e-6
+
+
+def test_next_row_helpers_pack_image_and_vertex_normals():
+    """image packing and vertex-normal recomputation on the device."""
+    import time
+    import neumesh_b200 as nb
+    from neumesh_b200.renderer import pack_bgr8, vertex_normals
+    dev = _dev()
+    rgb = torch.rand(5000, 3) * 1.2 - 0.1
+    got = pack_bgr8(rgb.to(dev)).cpu().numpy()
+    ref = (np.clip(rgb.numpy(), 0, 1) * 255).astype(np.uint8)[:, ::-1]   # render.py:219-241 + BGR for cv2
+    assert np.array_equal(got, ref)
+    mesh = synth.icosphere_mesh(6, seed=2)
+    n = vertex_normals(torch.from_numpy(mesh.vertices).float().to(dev), torch.from_numpy(mesh.triangles).to(dev))
+    assert (n.cpu().double() - torch.from_numpy(mesh.vertex_normals)).abs().max() < 2e-4   # fp32 atomics vs float64
+    # grid rebuild (what an editing tool triggers when it swaps the mesh): milliseconds, not the reference's O(V^2)
+    big = synth.icosphere_mesh(7, seed=0)
+    v = torch.from_numpy(big.vertices).float().to(dev)
+    nb.GridHandle(v)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    nb.GridHandle(v)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(f"octree rebuild over {v.shape[0]} vertices: {dt * 1e3:.2f} ms")
+    assert dt < 0.5
