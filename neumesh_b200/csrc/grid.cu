@@ -503,17 +503,21 @@ knn_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts
 __global__ void __launch_bounds__(128)
 knn_lists_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts, const float4* __restrict__ indicator,
                  float w1, const float* __restrict__ xyz, const int32_t* __restrict__ off,
-                 const int32_t* __restrict__ cnt, int64_t R, KnnOut out) {
-  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (r >= R) return;
+                 const int32_t* __restrict__ cnt, int64_t R, int seg, int max_seg, KnnOut out) {
+  // thread t = g * R + r handles entries [g * seg, (g + 1) * seg) of ray r's list (short serial chains)
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t r = t % R;
+  const int gseg = (int)(t / R);
+  if (gseg >= max_seg) return;
   const int64_t b = off[r];
-  const int n = cnt[r];
+  const int j_begin = gseg * seg;
+  const int n = min(cnt[r], j_begin + seg);
   float d2[KNN_K];
   int32_t ix[KNN_K];
-  for (int j = 0; j < n; ++j) {
+  for (int j = j_begin; j < n; ++j) {
     const int64_t p = b + j;
     const float qx = xyz[p * 3], qy = xyz[p * 3 + 1], qz = xyz[p * 3 + 2];
-    if (j == 0) {
+    if (j == j_begin) {
       knn_walk<KNN_K, false>(nodes, pts, qx, qy, qz, d2, ix);
     } else {
       warm_rerank<KNN_K>(pts, qx, qy, qz, d2, ix);
@@ -536,11 +540,13 @@ knn_lists_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pt
 }
 
 int launch_knn_lists(const nmb_grid* g, const float4* indicator_sorted, float w1, const float* xyz, const int32_t* off,
-                     const int32_t* cnt, int64_t R, int64_t M, KnnOut out, cudaStream_t stream) {
+                     const int32_t* cnt, int64_t R, int64_t M, int max_list, KnnOut out, cudaStream_t stream) {
   if (M <= 0 || R <= 0) return 0;
   ProfScope prof(PROF_KNN_LIST, M, stream);
-  knn_lists_kernel<<<(unsigned)ceil_div(R, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, xyz, off,
-                                                                  cnt, R, out);
+  const int seg = 16;
+  const int max_seg = (int)ceil_div(max_list, seg);
+  knn_lists_kernel<<<(unsigned)ceil_div(R * max_seg, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1,
+                                                                            xyz, off, cnt, R, seg, max_seg, out);
   NMB_LAUNCH_OK();
   return 0;
 }
@@ -600,22 +606,25 @@ bound_scan_kernel(const float4* __restrict__ nodes, const float4* __restrict__ p
   }
 }
 
-// Ray-ordered bounded-near/far scan.  near = min, far = max over the samples with ds < thresh, and the depths are
-// monotone in the sample index, so near is the FIRST hit scanning from the front and far the first hit scanning from
-// the back: samples between the two can change neither and are not evaluated.  Output-identical to the full scan.
+// Ray-ordered bounded-near/far scan.  near = min, far = max over the samples with ds < thresh.  The n_grid samples of a
+// ray are split into segments of BOUND_SEG consecutive samples, one thread each (t = g * R + r): a thread walks its
+// segment from the front to its first hit (candidate for near, atomicMin on the depth bits) and from the back to its
+// last hit (candidate for far, atomicMax); samples between the two cannot change either extremum and are not
+// evaluated, and samples in cells of the shell certificate grid are decided without evaluation.  Output-identical to
+// evaluating all samples; the serial chain per thread is at most BOUND_SEG walks (short tails even with few rays).
+constexpr int BOUND_SEG = 32;
+
 __global__ void __launch_bounds__(128)
 bound_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts,
                   const float4* __restrict__ indicator, float w1, const float* __restrict__ rays_o,
                   const float* __restrict__ dirs, const float* __restrict__ near, const float* __restrict__ far,
                   int64_t R, int n_grid, float thresh, int32_t* __restrict__ bnear, int32_t* __restrict__ bfar,
-                  ShellGrid shell, int two_sided) {
-  // two_sided = 0: one thread scans front then back.  two_sided = 1 (few rays): thread r scans from the front,
-  // thread R + r from the back; a ray has a hit from the front iff it has one from the back, so both extrema are set
-  // (or neither) exactly as in the one-thread version.
+                  ShellGrid shell) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (t >= R * (two_sided ? 2 : 1)) return;
   const int64_t r = t % R;
-  const int side = (int)(t / R);
+  const int s_begin = (int)(t / R) * BOUND_SEG;
+  if (s_begin >= n_grid) return;
+  const int s_end = min(s_begin + BOUND_SEG, n_grid);
   const float ox = rays_o[r * 3 + 0], oy = rays_o[r * 3 + 1], oz = rays_o[r * 3 + 2];
   const float dx = dirs[r * 3 + 0], dy = dirs[r * 3 + 1], dz = dirs[r * 3 + 2];
   const float nr = near[r], fr = far[r];
@@ -625,8 +634,8 @@ bound_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ p
   // returns the mesh distance at sample s, or +inf / -inf when the sample lies in a cell certified to be outside /
   // inside the shell
   auto ds_at = [&](int s, float& depth) {
-    const float t = linspace01(s, n_grid);
-    depth = __fadd_rn(__fmul_rn(nr, __fsub_rn(1.0f, t)), __fmul_rn(fr, t));  // renderer.py:81
+    const float tt = linspace01(s, n_grid);
+    depth = __fadd_rn(__fmul_rn(nr, __fsub_rn(1.0f, tt)), __fmul_rn(fr, tt));  // renderer.py:81
     const float qx = __fadd_rn(ox, __fmul_rn(depth, dx));
     const float qy = __fadd_rn(oy, __fmul_rn(depth, dy));
     const float qz = __fadd_rn(oz, __fmul_rn(depth, dz));
@@ -657,33 +666,23 @@ bound_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ p
   };
   int first = -1;
   float depth = 0.f;
-  if (side == 0) {
-    for (int s = 0; s < n_grid; ++s) {
-      if (ds_at(s, depth) < thresh) {
-        first = s;
-        bnear[r] = __float_as_int(depth);
-        break;
-      }
+  for (int s = s_begin; s < s_end; ++s) {
+    if (ds_at(s, depth) < thresh) {
+      first = s;
+      atomicMin(&bnear[r], __float_as_int(depth));   // depths are >= 0: their bit patterns order like the values
+      break;
     }
-    if (first < 0 || two_sided) return;  // no sample inside the shell: bnear / bfar keep their "unset" values
-  } else {
-    first = -1;   // back-scanning thread: stops at its own first hit (exists iff the front scan finds one)
-    for (int s = n_grid - 1; s >= 0; --s) {
-      if (ds_at(s, depth) < thresh) {
-        bfar[r] = __float_as_int(depth);
-        break;
-      }
-    }
-    return;
   }
-  for (int s = n_grid - 1; s >= first; --s) {
-    // s == first is known to be a hit: the loop always terminates with bfar set
-    if (s == first || ds_at(s, depth) < thresh) {
-      if (s == first) {
-        const float t = linspace01(s, n_grid);
-        depth = __fadd_rn(__fmul_rn(nr, __fsub_rn(1.0f, t)), __fmul_rn(fr, t));
-      }
-      bfar[r] = __float_as_int(depth);
+  if (first < 0) return;  // no hit in this segment
+  for (int s = s_end - 1; s >= first; --s) {
+    // s == first is known to be a hit: the loop always terminates with a far candidate
+    if (s == first) {
+      atomicMax(&bfar[r], __float_as_int(depth));   // `depth` still holds sample `first` unless overwritten below
+      break;
+    }
+    float dd;
+    if (ds_at(s, dd) < thresh) {
+      atomicMax(&bfar[r], __float_as_int(dd));
       break;
     }
   }
@@ -696,10 +695,10 @@ int launch_bound_scan(const nmb_grid* g, const float4* indicator, float w1, cons
   if (n <= 0) return 0;
   ProfScope prof(PROF_BOUND, n, stream);
   if (R >= RAY_KERNEL_MIN_RAYS) {
-    const int two_sided = (R < (int64_t)sm_count() * 2048) ? 1 : 0;
-    bound_rays_kernel<<<(unsigned)ceil_div(R * (two_sided ? 2 : 1), 128), 128, 0, stream>>>(
+    const int64_t nseg = ceil_div(n_grid, BOUND_SEG);
+    bound_rays_kernel<<<(unsigned)ceil_div(R * nseg, 128), 128, 0, stream>>>(
         g->nodes.p, g->pts.p, indicator, w1, rays_o, dirs, near, far, R, n_grid, thresh, bnear, bfar,
-        (thresh == 0.1f) ? shell : ShellGrid{}, two_sided);
+        (thresh == 0.1f) ? shell : ShellGrid{});
     NMB_LAUNCH_OK();
     return 0;
   }

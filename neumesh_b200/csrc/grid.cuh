@@ -65,7 +65,7 @@ int launch_bound_scan(const nmb_grid* g, const float4* indicator, float w1, cons
                       int32_t* bfar, ShellGrid shell, cudaStream_t stream);
 
 int launch_knn_lists(const nmb_grid* g, const float4* indicator_sorted, float w1, const float* xyz, const int32_t* off,
-                     const int32_t* cnt, int64_t R, int64_t M, KnnOut out, cudaStream_t stream);
+                     const int32_t* cnt, int64_t R, int64_t M, int max_list, KnnOut out, cudaStream_t stream);
 
 int launch_knn_distance(const nmb_grid* g, const float4* indicator_sorted, float w1, PointSrc src, int64_t P,
                         KnnOut out, cudaStream_t stream);

@@ -687,7 +687,7 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
           KnnOut ko{w.k_ds, w.k_slot, w.k_w, w.k_grad, M};
           int rc2;
           if (R >= 32768) {   // enough rays to fill the GPU with one thread per ray: warm-started per-ray lists
-            rc2 = launch_knn_lists(g, f->indicator.p, f->w1, xyz, w.live_off, w.nlive, R, M, ko, stream);
+            rc2 = launch_knn_lists(g, f->indicator.p, f->w1, xyz, w.live_off, w.nlive, R, M, P - 1, ko, stream);
           } else {
             PointSrc src{xyz, nullptr, nullptr, nullptr, 0};
             rc2 = launch_knn_distance(g, f->indicator.p, f->w1, src, M, ko, stream);
