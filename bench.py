@@ -428,7 +428,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
             "dtype": "fp32 (MLPs: 3xTF32 tcgen05, fp32 accumulate)" if args.engine == "tcgen05" else "fp32",
-            "data": "synthetic", "config": {**workload_config(n_rays), "parallelism": f"interleaved ray-shard x{world} + all_gather",
+            "data": "synthetic", "config": {**workload_config(n_rays), "parallelism": f"block-cyclic ray-shard x{world} + all_gather",
                                             "mlp_engine": args.engine,
                                             "skip_dead_samples": not args.all_samples},
             "e2e": {"value": e2e_val, "unit": "rays/s", "ms_per_step": ms_e2e / args.steps,
