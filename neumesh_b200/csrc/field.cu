@@ -5,13 +5,14 @@
 
 namespace nmb {
 
-__global__ void permute_table_kernel(const float* __restrict__ src, const int32_t* __restrict__ order, int64_t V,
+__global__ void permute_table_kernel(const float* __restrict__ src, const int32_t* __restrict__ order, int64_t V, int F,
                                      float* __restrict__ dst) {
-  // FEAT = 32 floats per row: one warp per row, coalesced both ways
+  // F = 32 n floats per row: one warp per row, coalesced both ways
   const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= V) return;
-  dst[row * FEAT + lane] = src[(int64_t)order[row] * FEAT + lane];
+  const float* s = src + (int64_t)order[row] * F;
+  for (int c = lane; c < F; c += 32) dst[row * F + c] = s[c];
 }
 
 // One block per output unit n: W_eff[n][:] = g[n] * v[n][:] / ||v[n]||  (or v itself when g == nullptr), written
@@ -55,12 +56,14 @@ static FieldLayout make_layout(const nmb_field_desc* d) {
   L.ch_d = 1 + 2 * L.Ld;
   L.ch_v = 3 * (1 + 2 * L.Lv);
   L.use_nabla = d->enable_nablas_input ? 1 : 0;
+  L.Fg = d->geometry_dim;
+  L.Fc = d->color_dim;
   L.off_fg = (int)align_up(L.ch_d, 16);
-  L.K0g = (int)align_up(L.off_fg + FEAT * (1 + 2 * L.Lfg), 16);
+  L.K0g = (int)align_up(L.off_fg + L.Fg * (1 + 2 * L.Lfg), 16);
   L.off_nabla = L.ch_d;
   L.off_view = L.ch_d + (L.use_nabla ? 3 : 0);
   L.off_ft = (int)align_up(L.off_view + L.ch_v, 16);
-  L.K0c = (int)align_up(L.off_ft + FEAT * (1 + 2 * L.Lft), 16);
+  L.K0c = (int)align_up(L.off_ft + L.Fc * (1 + 2 * L.Lft), 16);
   L.n_geo = d->D_density;
   L.n_col = d->D_color;
   return L;
@@ -70,7 +73,7 @@ static FieldLayout make_layout(const nmb_field_desc* d) {
 static std::vector<int32_t> geo_colmap(const FieldLayout& L) {
   std::vector<int32_t> m(L.K0g, -1);
   for (int i = 0; i < L.ch_d; ++i) m[i] = i;                                            // neumesh.py:214,217
-  for (int i = 0; i < FEAT * (1 + 2 * L.Lfg); ++i) m[L.off_fg + i] = L.ch_d + i;
+  for (int i = 0; i < L.Fg * (1 + 2 * L.Lfg); ++i) m[L.off_fg + i] = L.ch_d + i;
   return m;
 }
 static std::vector<int32_t> col_colmap(const FieldLayout& L) {
@@ -80,7 +83,7 @@ static std::vector<int32_t> col_colmap(const FieldLayout& L) {
   for (int i = 0; i < L.ch_d; ++i) m[i] = nb + i;
   for (int i = 0; i < nb; ++i) m[L.off_nabla + i] = i;
   for (int i = 0; i < L.ch_v; ++i) m[L.off_view + i] = nb + L.ch_d + i;
-  for (int i = 0; i < FEAT * (1 + 2 * L.Lft); ++i) m[L.off_ft + i] = nb + L.ch_d + L.ch_v + i;
+  for (int i = 0; i < L.Fc * (1 + 2 * L.Lft); ++i) m[L.off_ft + i] = nb + L.ch_d + L.ch_v + i;
   return m;
 }
 
@@ -126,7 +129,10 @@ static int pack_ffma(const float* const* v, const float* const* g, const float* 
 static int pack_field(const nmb_field_desc* d, nmb_field* f, cudaStream_t stream) {
   const nmb_grid* g = f->grid;
   NMB_CHECK(d->W == MLP_W, "fused kernels are specialised for W = 256");
-  NMB_CHECK(d->geometry_dim == FEAT && d->color_dim == FEAT, "fused kernels are specialised for 32-d vertex codes");
+  NMB_CHECK(d->geometry_dim >= FEAT && d->geometry_dim % FEAT == 0 && d->color_dim >= FEAT && d->color_dim % FEAT == 0,
+            "fused kernels need vertex code widths that are multiples of 32");
+  NMB_CHECK(f->engine == 0 || (d->geometry_dim == FEAT && d->color_dim == FEAT),
+            "the fp32 engine is specialised for 32-d vertex codes (use the tcgen05 engine)");
   NMB_CHECK(d->D_density >= 1 && d->D_density < MAX_LAYERS && d->D_color >= 1 && d->D_color < MAX_LAYERS,
             "unsupported MLP depth");
   NMB_CHECK(d->multires_d >= 0 && d->multires_fg >= 0 && d->multires_ft >= 0 && d->multires_view >= 0,
@@ -134,25 +140,26 @@ static int pack_field(const nmb_field_desc* d, nmb_field* f, cudaStream_t stream
   f->lay = make_layout(d);
   f->shell_valid = false;
   f->shell = ShellGrid{};
-  NMB_CHECK(f->lay.K0g <= 256 && f->lay.K0c <= 256, "first-layer width exceeds the fused kernels' 256-column tile");
+  NMB_CHECK(f->engine == 0 || (f->lay.K0g <= 256 && f->lay.K0c <= 256),
+            "first-layer width exceeds the fp32 engine's 256-column tile");
   f->w1 = d->indicator_weight;
   f->s = d->s;
   NMB_CUDA_OK(f->indicator.alloc(g->V));
-  NMB_CUDA_OK(f->fg.alloc(g->V * FEAT));
-  NMB_CUDA_OK(f->fc.alloc(g->V * FEAT));
+  NMB_CUDA_OK(f->fg.alloc(g->V * f->lay.Fg));
+  NMB_CUDA_OK(f->fc.alloc(g->V * f->lay.Fc));
   int rc = permute_indicator(g, d->indicator_vector, f->indicator.p, stream);
   if (rc) return rc;
   const unsigned blocks = (unsigned)ceil_div(g->V * 32, 256);
-  permute_table_kernel<<<blocks, 256, 0, stream>>>(d->geometry_features, g->order.p, g->V, f->fg.p);
+  permute_table_kernel<<<blocks, 256, 0, stream>>>(d->geometry_features, g->order.p, g->V, f->lay.Fg, f->fg.p);
   NMB_LAUNCH_OK();
-  permute_table_kernel<<<blocks, 256, 0, stream>>>(d->color_features, g->order.p, g->V, f->fc.p);
+  permute_table_kernel<<<blocks, 256, 0, stream>>>(d->color_features, g->order.p, g->V, f->lay.Fc, f->fc.p);
   NMB_LAUNCH_OK();
   const FieldLayout& L = f->lay;
-  rc = pack_ffma(d->geo_v, d->geo_g, d->geo_b, L.n_geo, 1, L.K0g, L.ch_d + FEAT * (1 + 2 * L.Lfg), geo_colmap(L),
+  rc = pack_ffma(d->geo_v, d->geo_g, d->geo_b, L.n_geo, 1, L.K0g, L.ch_d + L.Fg * (1 + 2 * L.Lfg), geo_colmap(L),
                  &f->geo_f, stream);
   if (rc) return rc;
   rc = pack_ffma(d->col_w, nullptr, d->col_b, L.n_col, 3, L.K0c,
-                 (L.use_nabla ? 3 : 0) + L.ch_d + L.ch_v + FEAT * (1 + 2 * L.Lft), col_colmap(L), &f->col_f, stream);
+                 (L.use_nabla ? 3 : 0) + L.ch_d + L.ch_v + L.Fc * (1 + 2 * L.Lft), col_colmap(L), &f->col_f, stream);
   if (rc) return rc;
   rc = pack_mlp_tc(d, L, f, stream);
   if (rc) return rc;

@@ -6,7 +6,7 @@
 namespace nmb {
 
 constexpr int MLP_W = 256;     // hidden width the fused kernels are specialised for
-constexpr int FEAT = 32;       // per-vertex code width the fused kernels are specialised for
+constexpr int FEAT = 32;       // feature block: vertex codes are processed 32 columns at a time (code width = 32 n)
 constexpr int MAX_LAYERS = 8;
 
 // Column layout of the first-layer inputs (our own order; weights are permuted to match at pack time).
@@ -19,6 +19,7 @@ struct FieldLayout {
   int off_nabla, off_view, off_ft, K0c;
   int n_geo, n_col;          // hidden layer counts
   int use_nabla;
+  int Fg, Fc;                // vertex code widths (multiples of FEAT; the fp32 engine handles 32 only)
 };
 
 struct MlpFfma {            // fp32 engine: W^T per layer, [K][256] row-major (k-major), zero rows for padding
@@ -46,8 +47,8 @@ struct nmb_field {
   nmb::FieldLayout lay{};
   float w1 = 0.1f, s = 1.f;
   nmb::DevBuf<float4> indicator;  // [V] sorted
-  nmb::DevBuf<float> fg;          // [V,32] sorted
-  nmb::DevBuf<float> fc;          // [V,32] sorted
+  nmb::DevBuf<float> fg;          // [V,Fg] sorted
+  nmb::DevBuf<float> fc;          // [V,Fc] sorted
   nmb::MlpFfma geo_f, col_f;
   nmb::MlpTc geo_t, col_t;
   // shell-free certificate grid (built lazily by the first large render after a (re)pack; csrc/shell.cu)

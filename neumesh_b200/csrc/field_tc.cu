@@ -512,6 +512,8 @@ mlp_tc_kernel(const tc::Params prm) {
     uint32_t it = 0;
     const int off_feat = (MODE == 2) ? L.off_ft : L.off_fg;   // multiple of 16
     const int Lf = (MODE == 2) ? L.Lft : L.Lfg;
+    const int Fdim = (MODE == 2) ? L.Fc : L.Fg;   // code width = n_fb blocks of FEAT columns
+    const int n_fb = Fdim / FEAT;
     const float* __restrict__ table = (MODE == 2) ? prm.tab.fc : prm.tab.fg;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int64_t p = tile * PTS + ((MODE == 1) ? (r & 63) : r);
@@ -526,20 +528,20 @@ mlp_tc_kernel(const tc::Params prm) {
         mbar_arrive(bar(A_FULL + slot));
         ++q;
       };
-      // ---- gather + blend of this half's 16 features (registers); issued before any ring wait so that its
-      //      latency overlaps the previous tile ----
+      // ---- gather + blend of this half's 16 features of code block fb (registers).  Block 0 is issued before any
+      //      ring wait so that its latency overlaps the previous tile ----
       float feat[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) feat[i] = 0.f;
       float ds = 0.f;
-      if (valid) {
-        ds = prm.in.ds[p];
-        if (!tangent) {
+      if (valid) ds = prm.in.ds[p];
+      auto gather = [&](int fb) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) feat[i] = 0.f;
+        if (valid && !tangent) {
 #pragma unroll
           for (int k = 0; k < KNN_K; ++k) {
             const int32_t sl = prm.in.slot[k * prm.in.stride + p];
             const float w = prm.in.w[k * prm.in.stride + p];
-            const float* row = table + (int64_t)sl * FEAT + 4 * h;
+            const float* row = table + (int64_t)sl * Fdim + fb * FEAT + 4 * h;
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {
               const float4 a = __ldg(reinterpret_cast<const float4*>(row + 8 * g4));
@@ -550,7 +552,8 @@ mlp_tc_kernel(const tc::Params prm) {
             }
           }
         }
-      }
+      };
+      gather(0);
       // ---- head block: columns [0, off_feat): PE(ds) [, nabla, PE(view)], zero padded ----
       {
         float head[64];
@@ -581,30 +584,33 @@ mlp_tc_kernel(const tc::Params prm) {
           emit(v);
         }
       }
-      // ---- raw features: slab s holds groups g = 2s, 2s+1: columns [8h, 8h+8) = feat[g = 2s][0..3], feat[2s+1][0..3] ----
+      for (int fb = 0; fb < n_fb; ++fb) {
+        if (fb > 0) gather(fb);
+        // ---- raw features: slab s holds groups g = 2s, 2s+1: columns [8h, 8h+8) = feat[g = 2s][0..3], feat[2s+1][0..3] ----
 #pragma unroll
-      for (int s2 = 0; s2 < 2; ++s2) {
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = feat[s2 * 8 + i];
-        emit(v);
-      }
-      // ---- bands: slab (b, g): columns [8h, 8h+8) = [sin(2^b f[g][0..3]), cos(2^b f[g][0..3])] ----
-      float fr = 1.f;
-      for (int b = 0; b < Lf; ++b) {
-#pragma unroll
-        for (int g4 = 0; g4 < 4; ++g4) {
+        for (int s2 = 0; s2 < 2; ++s2) {
           float v[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float sn = 0.f, cs = 0.f;
-            if (valid && !tangent) sincosf(feat[g4 * 4 + i] * fr, &sn, &cs);
-            v[i] = sn;
-            v[4 + i] = cs;
-          }
+          for (int i = 0; i < 8; ++i) v[i] = feat[s2 * 8 + i];
           emit(v);
         }
-        fr *= 2.f;
+        // ---- bands: slab (b, g): columns [8h, 8h+8) = [sin(2^b f[g][0..3]), cos(2^b f[g][0..3])] ----
+        float fr = 1.f;
+        for (int b = 0; b < Lf; ++b) {
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float sn = 0.f, cs = 0.f;
+              if (valid && !tangent) sincosf(feat[g4 * 4 + i] * fr, &sn, &cs);
+              v[i] = sn;
+              v[4 + i] = cs;
+            }
+            emit(v);
+          }
+          fr *= 2.f;
+        }
       }
     }
   } else if (warp == WARP_MMA) {
@@ -723,17 +729,21 @@ static std::vector<int32_t> tc_first_layer_map(const FieldLayout& L, bool color)
   const int Lf = color ? L.Lft : L.Lfg;
   std::vector<int32_t> m;
   for (int k = 0; k < off; ++k) m.push_back(k);                 // head block: identical order
+  const int Fdim = color ? L.Fc : L.Fg;
   auto F = [](int g, int h, int i) { return 8 * g + 4 * h + i; };
-  for (int s = 0; s < 2; ++s)
-    for (int h = 0; h < 2; ++h)
-      for (int u = 0; u < 2; ++u)
-        for (int i = 0; i < 4; ++i) m.push_back(off + F(2 * s + u, h, i));
-  for (int b = 0; b < Lf; ++b)
-    for (int g = 0; g < 4; ++g)
-      for (int h = 0; h < 2; ++h) {
-        for (int i = 0; i < 4; ++i) m.push_back(off + (1 + 2 * b) * FEAT + F(g, h, i));  // sin block
-        for (int i = 0; i < 4; ++i) m.push_back(off + (2 + 2 * b) * FEAT + F(g, h, i));  // cos block
-      }
+  for (int fb = 0; fb < Fdim / FEAT; ++fb) {   // one run of (2 raw + 4 Lf band) slabs per 32-column code block
+    const int f0 = fb * FEAT;
+    for (int s = 0; s < 2; ++s)
+      for (int h = 0; h < 2; ++h)
+        for (int u = 0; u < 2; ++u)
+          for (int i = 0; i < 4; ++i) m.push_back(off + f0 + F(2 * s + u, h, i));
+    for (int b = 0; b < Lf; ++b)
+      for (int g = 0; g < 4; ++g)
+        for (int h = 0; h < 2; ++h) {
+          for (int i = 0; i < 4; ++i) m.push_back(off + (1 + 2 * b) * Fdim + f0 + F(g, h, i));  // sin block
+          for (int i = 0; i < 4; ++i) m.push_back(off + (2 + 2 * b) * Fdim + f0 + F(g, h, i));  // cos block
+        }
+  }
   return m;
 }
 

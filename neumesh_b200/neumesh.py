@@ -107,7 +107,9 @@ class NeuMesh(nn.Module):
 
     def fused_supported(self) -> bool:
         c = self._cfg
-        return (c["W"] == 256 and c["geometry_dim"] == 32 and c["color_dim"] == 32 and c["input_view_dim"] == 3
+        wide = self.mlp_engine == "tcgen05"      # the fp32 engine is specialised for 32-d codes
+        dims_ok = all(d >= 32 and d % 32 == 0 and (wide or d == 32) for d in (c["geometry_dim"], c["color_dim"]))
+        return (c["W"] == 256 and dims_ok and c["input_view_dim"] == 3
                 and c["input_d_dim"] == 1 and min(c["multires_d"], c["multires_fg"], c["multires_ft"],
                                                   c["multires_view"]) >= 0
                 and hasattr(self.mesh_grid, "grid") and hasattr(self.mesh_grid.grid, "handle"))
@@ -121,7 +123,7 @@ class NeuMesh(nn.Module):
         covers tensor identity *and* in-place version counters."""
         if not self.fused_supported():
             raise RuntimeError("this NeuMesh configuration is outside the fused CUDA kernels' specialisation "
-                               "(W=256, 32-d vertex codes, non-negative multires)")
+                               "(W=256, vertex code widths that are multiples of 32 - exactly 32 for the fp32 engine -, non-negative multires)")
         params = list(self.parameters())
         key = (id(self.mesh_grid), id(self.mesh_grid.grid), self.mlp_engine, float(self.speed_factor),
                tuple((p.data_ptr(), p._version) for p in params))
