@@ -151,8 +151,8 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": workload_config(n),
+        "scaling": "strong" if (args.frames_per_step == 1 and world > 1) else "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic", "config": workload_config(n),
         "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
                          "sample": f"{n} rays strided over the 800x800 frame per step (oracle port of the reference "
                                    f"renderer, torch CPU fp32 + scipy cKDTree exact KNN, os.cpu_count()={os.cpu_count()})"},
@@ -182,6 +182,9 @@ def main():
     ap.add_argument("--simulate-world", type=int, default=1,
                     help="(diagnostic, 1 GPU) render only rank 0's block-cyclic share of an N-way split and print the "
                          "per-rank time: predicts N-GPU throughput without N GPUs; not a bench value")
+    ap.add_argument("--frames-per-step", type=int, default=0,
+                    help="spiral frames rendered per step, their rays pooled and block-cyclic-sharded over the ranks "
+                         "(default: one per GPU = fixed work per GPU, 'weak'; 1 = single-frame latency, 'strong')")
     ap.add_argument("--tune", action="store_true", help="(diagnostic) with --simulate-world 1: print per-class times only")
     ap.add_argument("--all-samples", action="store_true",
                     help="evaluate colour / nabla at every sample like the reference does, instead of only where the "
@@ -207,13 +210,18 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    n_frames = args.warmup + args.steps
-    cfg, mesh, sd, frames = build_inputs(min(n_frames, 90))
+    sim = max(1, args.simulate_world)                # single-GPU what-if: render only rank 0's share of a `sim`-way split
+    fps = 1 if (sim > 1 or args.tune) else (args.frames_per_step or world)
+    scaling = "strong" if (fps == 1 and world > 1) else "weak"
+    n_steps_in = max(1, min(args.warmup + args.steps, 90 // fps))      # distinct step inputs (90 spiral views)
+    cfg, mesh, sd, views = build_inputs(n_steps_in * fps)
+    frames = [(torch.cat([views[i * fps + j][0] for j in range(fps)]), torch.cat([views[i * fps + j][1] for j in range(fps)]))
+              for i in range(n_steps_in)]
+    del views
     model = nb.NeuMesh(nb.MeshGrid(mesh, dev), mlp_engine=args.engine, **cfg.model_kwargs())
     model.load_state_dict(sd)
     model = model.to(dev).eval()
-    n_rays = H * W
-    sim = max(1, args.simulate_world)                # single-GPU what-if: render only rank 0's share of a `sim`-way split
+    n_rays = H * W * fps                             # rays per step: `fps` consecutive spiral frames, pooled
     sl = parallel.shard_indices(n_rays, rank, world * sim)   # block-cyclic: every rank gets the same hit / miss mix
     n_mine = parallel.shard_count(n_rays, rank, world * sim)
     host = [(o[sl].contiguous().pin_memory(), d[sl].contiguous().pin_memory()) for o, d in frames]
@@ -426,9 +434,10 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None,
+            "scaling": scaling, "vs_baseline": None,
             "dtype": "fp32 (MLPs: 3xTF32 tcgen05, fp32 accumulate)" if args.engine == "tcgen05" else "fp32",
-            "data": "synthetic", "config": {**workload_config(n_rays), "parallelism": f"block-cyclic ray-shard x{world} + all_gather",
+            "data": "synthetic", "config": {**workload_config(n_rays), "frames_per_step": fps,
+                                            "parallelism": f"block-cyclic ray-shard x{world} + all_gather",
                                             "mlp_engine": args.engine,
                                             "skip_dead_samples": not args.all_samples},
             "e2e": {"value": e2e_val, "unit": "rays/s", "ms_per_step": ms_e2e / args.steps,
