@@ -12,14 +12,17 @@ static std::atomic<int64_t> g_launches{0};
 void set_error(const std::string& msg) { g_error = msg; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-    if (cached <= 0) cached = 148;
+  static std::atomic<int> cached[NMB_MAX_DEVICES];   // per device of this process; 0 = not queried yet
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::atomic<int>& c = cached[dev % NMB_MAX_DEVICES];
+  int n = c.load(std::memory_order_relaxed);
+  if (n == 0) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    c.store(n, std::memory_order_relaxed);
   }
-  return cached;
+  return n;
 }
 
 // ---- profiling ----

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <mutex>
 #include <string>
 
 namespace nmb {
@@ -33,6 +34,39 @@ void count_launch(int n = 1);
     ::nmb::count_launch();                                   \
     NMB_CUDA_OK(cudaGetLastError());                         \
   } while (0)
+
+// Stream-ordered scratch (cudaMallocAsync) that is returned to the pool on every exit path of an API call.
+struct StreamBuf {
+  void* p = nullptr;
+  cudaStream_t stream = nullptr;
+  StreamBuf() = default;
+  StreamBuf(const StreamBuf&) = delete;
+  StreamBuf& operator=(const StreamBuf&) = delete;
+  ~StreamBuf() {
+    if (p) cudaFreeAsync(p, stream);
+  }
+  cudaError_t alloc(size_t bytes, cudaStream_t s) {
+    stream = s;
+    return cudaMallocAsync(&p, bytes ? bytes : 1, s);
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+// Run `f` (-> cudaError_t) once per CUDA device of this process (kernel attributes are per device); thread-safe.
+constexpr int NMB_MAX_DEVICES = 64;
+struct DeviceOnce {
+  std::once_flag flags[NMB_MAX_DEVICES];
+  template <typename F>
+  cudaError_t run(F&& f) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    cudaError_t rc = cudaSuccess;
+    std::call_once(flags[dev % NMB_MAX_DEVICES], [&] { rc = f(); });
+    return rc;
+  }
+};
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t align_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }

@@ -209,8 +209,9 @@ static int field_query(const nmb_field* f, const float* xyz, const float* dirs, 
   if (M <= 0) return 0;
   const bool need_nabla = (nabla != nullptr) || (want_color && f->lay.use_nabla);
   // scratch: ds 1, slot 8, w 8, grad 3, nabla 3, rgb 3, sdf 1 = 27 words per point
-  float* sc = nullptr;
-  NMB_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&sc), sizeof(float) * M * 27, stream));
+  StreamBuf scratch;
+  NMB_CUDA_OK(scratch.alloc(sizeof(float) * M * 27, stream));
+  float* sc = scratch.as<float>();
   KnnOut ko{sc, reinterpret_cast<int32_t*>(sc + M), sc + 9 * M, sc + 17 * M, M};
   PointSrc src{xyz, nullptr, nullptr, nullptr, 0};
   int rc = launch_knn_distance(f->grid, f->indicator.p, f->w1, src, M, ko, stream);
@@ -238,7 +239,6 @@ static int field_query(const nmb_field* f, const float* xyz, const float* dirs, 
     soa3_to_rows_kernel<<<(unsigned)ceil_div(M * 3, 256), 256, 0, stream>>>(rgb_soa, M, M, rgb);
     NMB_LAUNCH_OK();
   }
-  NMB_CUDA_OK(cudaFreeAsync(sc, stream));
   return 0;
 }
 

@@ -226,11 +226,10 @@ static int launch_ffma(const nmb_field* f, const MlpFfma& mlp, const FieldIn& in
   prm.out1 = out1;
   constexpr int PTS = (MODE == 1) ? 32 : 64;
   const size_t smem = (256 * TM + 2 * KC * 256) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NMB_CUDA_OK(cudaFuncSetAttribute(mlp_ffma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static DeviceOnce attr_once;
+  NMB_CUDA_OK(attr_once.run([&] {
+    return cudaFuncSetAttribute(mlp_ffma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }));
   const int64_t tiles = ceil_div(P, PTS);
   const int64_t grid = tiles < (int64_t)2 * sm_count() ? tiles : (int64_t)2 * sm_count();
   ProfScope prof(MODE == 2 ? PROF_COLOR : (MODE == 1 ? PROF_GEO_JVP : PROF_GEO), P, stream);

@@ -809,19 +809,18 @@ static int launch_tc(const nmb_field* f, const MlpFfma& fm, const MlpTc& tm, con
   prm.out1 = out1;
   prm.dbg = nullptr;
   static const bool want_prof = getenv("NMB_TC_PROFILE") != nullptr;
-  static unsigned long long* dbg_dev = nullptr;
+  unsigned long long* dbg_dev = nullptr;   // diagnostics only: allocated per launch, the launch is synchronous then
   if (want_prof) {
-    if (!dbg_dev) NMB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&dbg_dev), 8 * sizeof(unsigned long long)));
+    NMB_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&dbg_dev), 8 * sizeof(unsigned long long)));
     NMB_CUDA_OK(cudaMemsetAsync(dbg_dev, 0, 8 * sizeof(unsigned long long), stream));
     prm.dbg = dbg_dev;
   }
   constexpr int PTS = (MODE == 1) ? 64 : 128;
   const size_t smem = tc::SmemLayout::total;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NMB_CUDA_OK(cudaFuncSetAttribute(mlp_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static DeviceOnce attr_once;
+  NMB_CUDA_OK(attr_once.run([&] {
+    return cudaFuncSetAttribute(mlp_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }));
   const int64_t tiles = ceil_div(P, PTS);
   int64_t grid = tiles < (int64_t)sm_count() ? tiles : (int64_t)sm_count();
   grid = align_up(grid, tc::CLUSTER);
@@ -840,6 +839,7 @@ static int launch_tc(const nmb_field* f, const MlpFfma& fm, const MlpTc& tm, con
             "MMA thread: total %.0f wait D_EMPTY %.0f wait A_FULL(L0) %.0f wait A_FULL(hidden) %.0f wait B_FULL %.0f\n",
             MODE, (long long)P, (long long)grid, h[2] / ne, h[0] / ne, h[1] / ne, h[7] / nm, h[3] / nm, h[4] / nm,
             h[5] / nm, h[6] / nm);
+    cudaFree(dbg_dev);
   }
   return 0;
 }

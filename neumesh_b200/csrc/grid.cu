@@ -860,10 +860,11 @@ int nmb_mesh_distance(const nmb_grid* g, const float* indicator, float indicator
   if (M <= 0) return 0;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   // scratch: permuted indicator + SoA outputs (API convenience path; the renderer uses packed fields instead)
-  float4* ind = nullptr;
-  float* soa = nullptr;
-  NMB_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&ind), sizeof(float4) * g->V, stream));
-  NMB_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&soa), sizeof(float) * M * 20, stream));
+  nmb::StreamBuf ind_buf, soa_buf;
+  NMB_CUDA_OK(ind_buf.alloc(sizeof(float4) * g->V, stream));
+  NMB_CUDA_OK(soa_buf.alloc(sizeof(float) * M * 20, stream));
+  float4* ind = ind_buf.as<float4>();
+  float* soa = soa_buf.as<float>();
   int rc = nmb::permute_indicator(g, indicator, ind, stream);
   if (rc) return rc;
   nmb::KnnOut out;
@@ -878,8 +879,6 @@ int nmb_mesh_distance(const nmb_grid* g, const float* indicator, float indicator
   nmb::export_knn_kernel<<<(unsigned)nmb::ceil_div(M * nmb::KNN_K, 256), 256, 0, stream>>>(g->order.p, out, M, ds, idx,
                                                                                         w, grad_ds);
   NMB_LAUNCH_OK();
-  NMB_CUDA_OK(cudaFreeAsync(ind, stream));
-  NMB_CUDA_OK(cudaFreeAsync(soa, stream));
   return 0;
 }
 

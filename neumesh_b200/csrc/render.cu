@@ -575,11 +575,17 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
   void* sort_tmp = nullptr;
   size_t sort_bytes = 0;
   NMB_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, key_in, key_out, idx_in, perm_all, (int)N, 0, 30, stream));
-  NMB_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&key_in), sizeof(uint32_t) * N, stream));
-  NMB_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&key_out), sizeof(uint32_t) * N, stream));
-  NMB_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&idx_in), sizeof(int32_t) * N, stream));
-  NMB_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&perm_all), sizeof(int32_t) * N, stream));
-  NMB_CUDA_OK(cudaMallocAsync(&sort_tmp, sort_bytes, stream));
+  StreamBuf b_key_in, b_key_out, b_idx_in, b_perm, b_sort;   // returned to the pool on every exit path
+  NMB_CUDA_OK(b_key_in.alloc(sizeof(uint32_t) * N, stream));
+  NMB_CUDA_OK(b_key_out.alloc(sizeof(uint32_t) * N, stream));
+  NMB_CUDA_OK(b_idx_in.alloc(sizeof(int32_t) * N, stream));
+  NMB_CUDA_OK(b_perm.alloc(sizeof(int32_t) * N, stream));
+  NMB_CUDA_OK(b_sort.alloc(sort_bytes, stream));
+  key_in = b_key_in.as<uint32_t>();
+  key_out = b_key_out.as<uint32_t>();
+  idx_in = b_idx_in.as<int32_t>();
+  perm_all = b_perm.as<int32_t>();
+  sort_tmp = b_sort.p;
   ray_key_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, stream>>>(rays_o, rays_d, N, cfg->obj_bounding_radius, key_in, idx_in);
   NMB_LAUNCH_OK();
   NMB_CUDA_OK(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, key_in, key_out, idx_in, perm_all, (int)N, 0, 30, stream));
@@ -746,11 +752,6 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
       }
     }
   }
-  NMB_CUDA_OK(cudaFreeAsync(key_in, stream));
-  NMB_CUDA_OK(cudaFreeAsync(key_out, stream));
-  NMB_CUDA_OK(cudaFreeAsync(idx_in, stream));
-  NMB_CUDA_OK(cudaFreeAsync(perm_all, stream));
-  NMB_CUDA_OK(cudaFreeAsync(sort_tmp, stream));
   return 0;
 }
 

@@ -33,6 +33,16 @@ def _workspace(device, nbytes):
     return ws
 
 
+def release_workspace(device: Optional[torch.device] = None) -> None:
+    """Drop the cached ``nmb_render`` scratch of ``device`` (all devices when None).  The fused path keeps one scratch
+    tensor per device sized for the largest chunk rendered so far (~21 GB at the default 2^20-ray chunk)."""
+    if device is None:
+        _WORKSPACES.clear()
+    else:
+        device = torch.device(device)
+        _WORKSPACES.pop((device.type, device.index), None)
+
+
 def fused_eligible(model, rays_o, *, batched, perturb, random_color_direction, use_view_dirs, N_samples, N_importance,
                    N_upsample_iters, samples_output) -> bool:
     if not isinstance(model, NeuMesh) or torch.is_grad_enabled() or not rays_o.is_cuda:
