@@ -25,6 +25,23 @@ int sm_count() {
   return n;
 }
 
+cudaError_t ensure_scratch_pool() {
+  static DeviceOnce once;
+  return once.run([] {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    cudaMemPool_t pool;
+    e = cudaDeviceGetDefaultMemPool(&pool, dev);
+    if (e != cudaSuccess) return e;
+    uint64_t cur = 0;
+    e = cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur);
+    if (e != cudaSuccess) return e;
+    uint64_t want = 1ull << 30;
+    return cur >= want ? cudaSuccess : cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &want);
+  });
+}
+
 // ---- profiling ----
 struct ProfRec {
   cudaEvent_t a, b;

@@ -35,6 +35,10 @@ void count_launch(int n = 1);
     NMB_CUDA_OK(cudaGetLastError());                         \
   } while (0)
 
+// Keeps up to 1 GiB of freed stream-ordered scratch cached in the device's default memory pool (the default
+// threshold of 0 hands every block back to the driver at the next synchronisation).  Once per device.
+cudaError_t ensure_scratch_pool();
+
 // Stream-ordered scratch (cudaMallocAsync) that is returned to the pool on every exit path of an API call.
 struct StreamBuf {
   void* p = nullptr;
@@ -47,6 +51,8 @@ struct StreamBuf {
   }
   cudaError_t alloc(size_t bytes, cudaStream_t s) {
     stream = s;
+    cudaError_t e = ensure_scratch_pool();
+    if (e != cudaSuccess) return e;
     return cudaMallocAsync(&p, bytes ? bytes : 1, s);
   }
   template <typename T>

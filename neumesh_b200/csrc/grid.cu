@@ -247,8 +247,9 @@ static int build_grid(const float* vertices, int64_t V, cudaStream_t stream, nmb
   const int64_t blocks = ceil_div(V, threads);
 
   // bounding cube
-  DevBuf<float> bb;
-  NMB_CUDA_OK(bb.alloc(6));
+  StreamBuf bb_buf;
+  NMB_CUDA_OK(bb_buf.alloc(6 * sizeof(float), stream));
+  struct { float* p; } bb{bb_buf.as<float>()};
   {
     int init[6] = {0x7f7fffff, 0x7f7fffff, 0x7f7fffff, (int)0x80800000, (int)0x80800000, (int)0x80800000};
     // ordered-int encodings of +FLT_MAX / -FLT_MAX
@@ -282,11 +283,13 @@ static int build_grid(const float* vertices, int64_t V, cudaStream_t stream, nmb
   const int L = g->levels;
 
   // Morton sort
-  DevBuf<uint32_t> code_in, code;
-  DevBuf<int32_t> iota;
-  NMB_CUDA_OK(code_in.alloc(V));
-  NMB_CUDA_OK(code.alloc(V));
-  NMB_CUDA_OK(iota.alloc(V));
+  // build temporaries are stream-ordered scratch (cached in the device pool: a rebuild allocates nothing new)
+  StreamBuf code_in_b, code_b, iota_b;
+  NMB_CUDA_OK(code_in_b.alloc(sizeof(uint32_t) * V, stream));
+  NMB_CUDA_OK(code_b.alloc(sizeof(uint32_t) * V, stream));
+  NMB_CUDA_OK(iota_b.alloc(sizeof(int32_t) * V, stream));
+  struct { uint32_t* p; } code_in{code_in_b.as<uint32_t>()}, code{code_b.as<uint32_t>()};
+  struct { int32_t* p; } iota{iota_b.as<int32_t>()};
   NMB_CUDA_OK(g->order.alloc(V));
   NMB_CUDA_OK(g->inv.alloc(V));
   NMB_CUDA_OK(g->pts.alloc(V));
@@ -297,12 +300,11 @@ static int build_grid(const float* vertices, int64_t V, cudaStream_t stream, nmb
     size_t tmp_bytes = 0;
     NMB_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, code_in.p, code.p, iota.p, g->order.p, (int)V, 0,
                                                 3 * L, stream));
-    DevBuf<char> tmp;
-    NMB_CUDA_OK(tmp.alloc((int64_t)tmp_bytes));
+    StreamBuf tmp;
+    NMB_CUDA_OK(tmp.alloc(tmp_bytes, stream));
     NMB_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, code_in.p, code.p, iota.p, g->order.p, (int)V, 0,
                                                 3 * L, stream));
     count_launch(4);
-    NMB_CUDA_OK(cudaStreamSynchronize(stream));
   }
   gather_points_kernel<<<(unsigned)blocks, threads, 0, stream>>>(vertices, g->order.p, V, g->pts.p, g->inv.p);
   NMB_LAUNCH_OK();
@@ -311,19 +313,16 @@ static int build_grid(const float* vertices, int64_t V, cudaStream_t stream, nmb
   // leaf capacity (points per leaf): tunable for experiments, default LEAF_MAX
   const int leaf_max = getenv("NMB_LEAF_MAX") ? std::max(1, atoi(getenv("NMB_LEAF_MAX"))) : LEAF_MAX;
   const int64_t cap = V + (int64_t)(L + 1) * (V / (leaf_max + 1) + 1) + 16;
-  DevBuf<int32_t> nbegin, nend, nfirst, nlast, pnode, newnode, head, cid;
-  NMB_CUDA_OK(nbegin.alloc(cap));
-  NMB_CUDA_OK(nend.alloc(cap));
-  NMB_CUDA_OK(nfirst.alloc(cap));
-  NMB_CUDA_OK(nlast.alloc(cap));
-  NMB_CUDA_OK(pnode.alloc(V));
-  NMB_CUDA_OK(newnode.alloc(V));
-  NMB_CUDA_OK(head.alloc(V));
-  NMB_CUDA_OK(cid.alloc(V + 1));
+  StreamBuf node_b, point_b;   // 4 node arrays of `cap` entries; 4 per-point arrays
+  NMB_CUDA_OK(node_b.alloc(sizeof(int32_t) * 4 * cap, stream));
+  NMB_CUDA_OK(point_b.alloc(sizeof(int32_t) * (4 * V + 4), stream));
+  struct I32 { int32_t* p; };
+  I32 nbegin{node_b.as<int32_t>()}, nend{nbegin.p + cap}, nfirst{nend.p + cap}, nlast{nfirst.p + cap};
+  I32 pnode{point_b.as<int32_t>()}, newnode{pnode.p + V}, head{newnode.p + V}, cid{head.p + V};
   size_t scan_bytes = 0;
   NMB_CUDA_OK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, head.p, cid.p, (int)V, stream));
-  DevBuf<char> scan_tmp;
-  NMB_CUDA_OK(scan_tmp.alloc((int64_t)scan_bytes));
+  StreamBuf scan_tmp;
+  NMB_CUDA_OK(scan_tmp.alloc(scan_bytes, stream));
 
   std::vector<int32_t> lvl_off;  // first node id of each level
   lvl_off.push_back(0);
