@@ -103,6 +103,21 @@ int nmb_field_sdf(const nmb_field* f, const float* xyz /*[M,3]*/, int64_t M, flo
 /* NeuMesh.forward (neumesh.py:113-138, need_nablas=True): sdf [M], rgb [M,3], nabla [M,3] nullable. */
 int nmb_field_forward(const nmb_field* f, const float* xyz, const float* view_dirs, int64_t M, float* sdf,
                       float* rgb, float* nabla, void* stream);
+/* NeuMesh.forward(..., nablas_only / return_ds=True) as the texture editors call it (neumesh.py:113-138,176-202;
+ * editing/texture_neumesh/texture_neumesh.py:66-72): the same evaluation, additionally returning the neighbour data:
+ * ds [M], idx [M,8] int64 (original vertex order), w [M,8].  view_dirs and rgb are both NULL (no colour) or both given;
+ * nabla, ds, idx, w are each nullable. */
+int nmb_field_forward_ex(const nmb_field* f, const float* xyz, const float* view_dirs, int64_t M, float* sdf,
+                         float* rgb, float* nabla, float* ds, int64_t* idx, float* w, void* stream);
+/* NeuMesh.forward_color(d, view_dirs, color_features, indices, weights, nabla) (neumesh.py:156-168,239-260): the colour
+ * network of `f` on caller-supplied neighbours - ds [M], idx [M,8] int64, w [M,8], nabla [M,3] (required iff the field
+ * was packed with enable_nablas_input), view_dirs [M,3] -> rgb [M,3].  color_table == NULL blends the field's own colour
+ * codes (idx = vertex ids of the field's mesh); otherwise `color_table` is a device [table_rows, color_dim] fp32 table in
+ * original row order and idx indexes its rows (texture_neumesh.py:104-111 passes another mesh's codes this way; ids
+ * outside [0, table_rows) are clamped). */
+int nmb_field_color(const nmb_field* f, const float* color_table, int64_t table_rows, const float* ds,
+                    const int64_t* idx, const float* w, const float* nabla, const float* view_dirs, int64_t M,
+                    float* rgb, void* stream);
 
 /* Shell-free certificate grid used by nmb_render's bounded near/far scan (csrc/shell.cu): builds it if necessary and
  * copies the G^3 bytes to `cells` (device, may be NULL to query the size only).  cells[(z*G + y)*G + x] == 1 means:

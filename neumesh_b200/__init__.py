@@ -14,6 +14,7 @@ extension is missing: there is no CPU fallback.
 from .mesh_grid import GridHandle, MeshGrid, MeshPrimitive, frnn_grid_points  # noqa: F401
 from .neumesh import Embedder, NeuMesh, get_embedder, interpolation  # noqa: F401
 from .renderer import SingleRenderer, release_workspace, volume_render  # noqa: F401
+from .texture_neumesh import TextureEditableNeuMesh  # noqa: F401
 
-__all__ = ["NeuMesh", "MeshGrid", "MeshPrimitive", "GridHandle", "frnn_grid_points", "volume_render", "release_workspace",
+__all__ = ["NeuMesh", "MeshGrid", "MeshPrimitive", "GridHandle", "frnn_grid_points", "volume_render", "release_workspace", "TextureEditableNeuMesh",
            "SingleRenderer", "Embedder", "get_embedder", "interpolation"]

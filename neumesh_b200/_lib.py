@@ -64,6 +64,8 @@ SIGNATURES = {
     "nmb_field_shell_grid": (C.c_int, [_P, _P, C.POINTER(_I32), C.POINTER(_F), _P]),
     "nmb_field_sdf": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
     "nmb_field_forward": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P]),
+    "nmb_field_forward_ex": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _P, _P, _P]),
+    "nmb_field_color": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P, _P, _I64, _P, _P]),
     "nmb_render_workspace_bytes": (_I64, [C.POINTER(RenderCfg), _I64]),
     "nmb_render": (C.c_int, [_P, C.POINTER(RenderCfg), _P, _P, _I64, _I64, _P, _P, _P, _P, C.POINTER(RenderDetail),
                              _P, _I64, _P]),

@@ -174,6 +174,23 @@ __global__ void soa3_to_rows_kernel(const float* __restrict__ soa, int64_t strid
   rows[t] = soa[(t % 3) * stride + t / 3];
 }
 
+// caller-supplied neighbours (row-major, original vertex order) -> the SoA the field kernels read
+__global__ void import_neighbours_kernel(const int64_t* __restrict__ idx /*[M,8]*/, const float* __restrict__ w /*[M,8]*/,
+                                         const float* __restrict__ nabla /*[M,3] or null*/,
+                                         const int32_t* __restrict__ inv /*vertex -> slot, or null = identity*/,
+                                         int64_t rows, int64_t M, int32_t* __restrict__ slot /*[8][M]*/,
+                                         float* __restrict__ w_soa /*[8][M]*/, float* __restrict__ nabla_soa /*[3][M]*/) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= M * KNN_K) return;
+  const int64_t m = t / KNN_K;
+  const int k = (int)(t % KNN_K);
+  int64_t v = idx[t];
+  v = v < 0 ? 0 : (v >= rows ? rows - 1 : v);   // never read outside the table, whatever the caller passed
+  slot[k * M + m] = inv ? inv[v] : (int32_t)v;
+  w_soa[k * M + m] = w[t];
+  if (k < 3 && nabla) nabla_soa[k * M + m] = nabla[m * 3 + k];
+}
+
 }  // namespace nmb
 
 extern "C" {
@@ -203,7 +220,8 @@ int nmb_field_update(nmb_field* f, const nmb_field_desc* desc, void* stream) {
 }
 
 static int field_query(const nmb_field* f, const float* xyz, const float* dirs, int64_t M, float* sdf, float* rgb,
-                       float* nabla, bool want_color, cudaStream_t stream) {
+                       float* nabla, bool want_color, cudaStream_t stream, float* ds_out = nullptr,
+                       int64_t* idx_out = nullptr, float* w_out = nullptr) {
   using namespace nmb;
   NMB_CHECK(f != nullptr, "null field");
   if (M <= 0) return 0;
@@ -216,6 +234,10 @@ static int field_query(const nmb_field* f, const float* xyz, const float* dirs, 
   PointSrc src{xyz, nullptr, nullptr, nullptr, 0};
   int rc = launch_knn_distance(f->grid, f->indicator.p, f->w1, src, M, ko, stream);
   if (rc) return rc;
+  if (ds_out || idx_out || w_out) {
+    rc = launch_export_knn(f->grid, ko, M, ds_out, idx_out, w_out, nullptr, stream);
+    if (rc) return rc;
+  }
   FieldIn in{};
   in.ds = ko.ds;
   in.slot = ko.slot;
@@ -264,6 +286,49 @@ int nmb_field_forward(const nmb_field* f, const float* xyz, const float* view_di
                       float* nabla, void* stream) {
   NMB_CHECK(view_dirs != nullptr && rgb != nullptr, "view_dirs and rgb are required");
   return field_query(f, xyz, view_dirs, M, sdf, rgb, nabla, true, static_cast<cudaStream_t>(stream));
+}
+
+int nmb_field_forward_ex(const nmb_field* f, const float* xyz, const float* view_dirs, int64_t M, float* sdf, float* rgb,
+                         float* nabla, float* ds, int64_t* idx, float* w, void* stream) {
+  NMB_CHECK((view_dirs != nullptr) == (rgb != nullptr), "view_dirs and rgb go together (both or neither)");
+  return field_query(f, xyz, view_dirs, M, sdf, rgb, nabla, rgb != nullptr, static_cast<cudaStream_t>(stream), ds, idx,
+                     w);
+}
+
+int nmb_field_color(const nmb_field* f, const float* color_table, int64_t table_rows, const float* ds,
+                    const int64_t* idx, const float* w, const float* nabla, const float* view_dirs, int64_t M, float* rgb,
+                    void* stream_) {
+  using namespace nmb;
+  NMB_CHECK(f != nullptr && ds && idx && w && view_dirs && rgb, "null argument");
+  NMB_CHECK(!f->lay.use_nabla || nabla != nullptr, "this field's colour network takes nabla as an input");
+  NMB_CHECK(color_table == nullptr || table_rows > 0, "table_rows must be positive when a table is given");
+  if (M <= 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  // scratch: slot 8, w 8, nabla 3, rgb 3 words per point
+  StreamBuf scratch;
+  NMB_CUDA_OK(scratch.alloc(sizeof(float) * M * 22, stream));
+  float* sc = scratch.as<float>();
+  int32_t* slot = reinterpret_cast<int32_t*>(sc);
+  float* w_soa = sc + 8 * M;
+  float* nab = sc + 16 * M;
+  float* rgb_soa = sc + 19 * M;
+  import_neighbours_kernel<<<(unsigned)ceil_div(M * KNN_K, 256), 256, 0, stream>>>(
+      idx, w, f->lay.use_nabla ? nabla : nullptr, color_table ? nullptr : f->grid->inv.p,
+      color_table ? table_rows : f->grid->V, M, slot, w_soa, nab);
+  NMB_LAUNCH_OK();
+  FieldIn in{};
+  in.ds = ds;
+  in.slot = slot;
+  in.w = w_soa;
+  in.stride = M;
+  in.nabla = nab;
+  in.dirs = view_dirs;
+  in.color_table = color_table;
+  int rc = launch_color(f, in, M, rgb_soa, stream);
+  if (rc) return rc;
+  soa3_to_rows_kernel<<<(unsigned)ceil_div(M * 3, 256), 256, 0, stream>>>(rgb_soa, M, M, rgb);
+  NMB_LAUNCH_OK();
+  return 0;
 }
 
 }  // extern "C"

@@ -72,6 +72,7 @@ struct FieldIn {
   const float* dirs;      // explicit [P,3] row-major view directions, or nullptr -> rays_d[p % R]
   const float* rays_d;    // [R,3]
   int64_t R;
+  const float* color_table;   // colour only: [rows, Fc] table indexed by `slot` instead of the field's own (nullable)
 };
 
 // geometry: sdf [P]; if nabla != nullptr also nabla [3][P] (SoA, stride = in.stride)

@@ -211,7 +211,7 @@ static int launch_ffma(const nmb_field* f, const MlpFfma& mlp, const FieldIn& in
   FfmaParams prm;
   prm.lay = f->lay;
   prm.in = in;
-  prm.tab = FieldTables{f->fg.p, f->fc.p};
+  prm.tab = FieldTables{f->fg.p, in.color_table ? in.color_table : f->fc.p};
   prm.w = mlp.w.p;
   prm.b = mlp.b.p;
   prm.w_out = mlp.w_out.p;

@@ -792,7 +792,7 @@ static int launch_tc(const nmb_field* f, const MlpFfma& fm, const MlpTc& tm, con
   tc::Params prm;
   prm.lay = f->lay;
   prm.in = in;
-  prm.tab = FieldTables{f->fg.p, f->fc.p};
+  prm.tab = FieldTables{f->fg.p, in.color_table ? in.color_table : f->fc.p};
   prm.w = tm.w.p;
   prm.bias = fm.b.p;
   prm.w_out = fm.w_out.p;

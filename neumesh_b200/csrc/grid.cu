@@ -797,6 +797,14 @@ __global__ void export_knn_kernel(const int32_t* __restrict__ order, KnnOut in, 
   if (k < 3 && grad) grad[m * 3 + k] = in.grad[k * in.stride + m];
 }
 
+int launch_export_knn(const nmb_grid* g, KnnOut in, int64_t M, float* ds, int64_t* idx, float* w, float* grad,
+                      cudaStream_t stream) {
+  if (M <= 0) return 0;
+  export_knn_kernel<<<(unsigned)ceil_div(M * KNN_K, 256), 256, 0, stream>>>(g->order.p, in, M, ds, idx, w, grad);
+  NMB_LAUNCH_OK();
+  return 0;
+}
+
 __global__ void permute_rows4_kernel(const float* __restrict__ src /*[V,3]*/, const int32_t* __restrict__ order,
                                      int64_t V, float4* __restrict__ dst) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -875,10 +883,7 @@ int nmb_mesh_distance(const nmb_grid* g, const float* indicator, float indicator
   nmb::PointSrc src{xyz, nullptr, nullptr, nullptr, 0};
   rc = nmb::launch_knn_distance(g, ind, indicator_weight, src, M, out, stream);
   if (rc) return rc;
-  nmb::export_knn_kernel<<<(unsigned)nmb::ceil_div(M * nmb::KNN_K, 256), 256, 0, stream>>>(g->order.p, out, M, ds, idx,
-                                                                                        w, grad_ds);
-  NMB_LAUNCH_OK();
-  return 0;
+  return nmb::launch_export_knn(g, out, M, ds, idx, w, grad_ds, stream);
 }
 
 }  // extern "C"

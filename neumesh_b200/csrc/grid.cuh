@@ -70,4 +70,8 @@ int launch_knn_lists(const nmb_grid* g, const float4* indicator_sorted, float w1
 int launch_knn_distance(const nmb_grid* g, const float4* indicator_sorted, float w1, PointSrc src, int64_t P,
                         KnnOut out, cudaStream_t stream);
 
+// SoA neighbour data (sorted slots) -> the reference's row-major outputs in original vertex order; any output may be null
+int launch_export_knn(const nmb_grid* g, KnnOut in, int64_t M, float* ds, int64_t* idx, float* w, float* grad,
+                      cudaStream_t stream);
+
 }  // namespace nmb

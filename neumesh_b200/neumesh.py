@@ -198,7 +198,9 @@ class NeuMesh(nn.Module):
         return (not torch.is_grad_enabled()) and all(t.is_cuda for t in tensors) and self.fused_supported() \
             and self.geometry_features.is_cuda
 
-    def _fused_query(self, xyz, view_dirs=None, want_nabla=False):
+    def _fused_query(self, xyz, view_dirs=None, want_nabla=False, want_neighbours=False):
+        """-> (sdf [...,1], nabla [...,3] | None, rgb [...,3] | None, neighbours) where neighbours is () or
+        (ds [...,1], indices [...,8] int64, weights [...,8]) as ``forward(..., return_ds=True)`` returns them."""
         lead = xyz.shape[:-1]
         flat = xyz.detach().reshape(-1, 3).float().contiguous()
         M = flat.shape[0]
@@ -206,30 +208,37 @@ class NeuMesh(nn.Module):
         field = self.packed_field()
         sdf = torch.empty(M, 1, device=dev)
         nabla = torch.empty(M, 3, device=dev) if want_nabla else None
-        with torch.cuda.device(dev):
-            if view_dirs is None:
-                _lib.check(_lib.lib().nmb_field_sdf(field, _lib.ptr(flat), M, _lib.ptr(sdf), _lib.ptr(nabla),
-                                                    _lib.stream_ptr(dev)))
-                rgb = None
-            else:
-                dirs = view_dirs.detach().reshape(-1, 3).float().contiguous()
-                rgb = torch.empty(M, 3, device=dev)
-                _lib.check(_lib.lib().nmb_field_forward(field, _lib.ptr(flat), _lib.ptr(dirs), M, _lib.ptr(sdf),
-                                                        _lib.ptr(rgb), _lib.ptr(nabla), _lib.stream_ptr(dev)))
-                rgb = rgb.reshape(*lead, 3)
-        return sdf.reshape(*lead, 1), (nabla.reshape(*lead, 3) if want_nabla else None), rgb
+        rgb = dirs = None
+        if view_dirs is not None:
+            dirs = view_dirs.detach().reshape(-1, 3).float().contiguous()
+            rgb = torch.empty(M, 3, device=dev)
+        ds = idx = w = None
+        if want_neighbours:
+            ds = torch.empty(M, 1, device=dev)
+            idx = torch.empty(M, 8, dtype=torch.int64, device=dev)
+            w = torch.empty(M, 8, device=dev)
+        if M > 0:
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().nmb_field_forward_ex(field, _lib.ptr(flat), _lib.ptr(dirs), M, _lib.ptr(sdf),
+                                                           _lib.ptr(rgb), _lib.ptr(nabla), _lib.ptr(ds), _lib.ptr(idx),
+                                                           _lib.ptr(w), _lib.stream_ptr(dev)))
+        nbr = (ds.reshape(*lead, 1), idx.reshape(*lead, 8), w.reshape(*lead, 8)) if want_neighbours else ()
+        return (sdf.reshape(*lead, 1), (nabla.reshape(*lead, 3) if want_nabla else None),
+                (rgb.reshape(*lead, 3) if rgb is not None else None), nbr)
 
     # ------------------------------------------------------------------------------------------------------
     # reference protocol (neumesh.py:113-174, 262-273)
     # ------------------------------------------------------------------------------------------------------
     def forward(self, xyz, view_dirs, need_nablas=True, nablas_only=False, return_ds=False):
-        if self._fused_ok(xyz, view_dirs) and not return_ds:
+        if self._fused_ok(xyz, view_dirs):
             if nablas_only:
-                sdf, nabla, _ = self._fused_query(xyz, None, want_nabla=need_nablas)
-                return sdf, (nabla if need_nablas else torch.zeros_like(sdf))
+                sdf, nabla, _, nbr = self._fused_query(xyz, None, want_nabla=need_nablas,
+                                                       want_neighbours=return_ds)
+                return (sdf, (nabla if need_nablas else torch.zeros_like(sdf))) + nbr
             if need_nablas or not self.enable_nablas_input:
-                sdf, _, rgb = self._fused_query(xyz, view_dirs, want_nabla=False)
-                return sdf, rgb
+                sdf, _, rgb, nbr = self._fused_query(xyz, view_dirs, want_nabla=False,
+                                                     want_neighbours=return_ds)
+                return (sdf, rgb) + nbr
         if need_nablas:
             xyz.requires_grad_(True)
         with (torch.enable_grad() if need_nablas else contextlib.nullcontext()):
@@ -252,7 +261,7 @@ class NeuMesh(nn.Module):
 
     def forward_with_nablas(self, xyz):
         if self._fused_ok(xyz):
-            sdf, nabla, _ = self._fused_query(xyz, None, want_nabla=True)
+            sdf, nabla, _, _ = self._fused_query(xyz, None, want_nabla=True)
             return sdf, nabla
         xyz.requires_grad_(True)
         with torch.enable_grad():
@@ -261,7 +270,36 @@ class NeuMesh(nn.Module):
         return density, nablas
 
     def forward_color(self, d, view_dirs, color_features, indices=None, weights=None, nabla=None):
+        """Colour network on caller-supplied neighbours (``neumesh.py:156-168``); ``color_features`` may be this
+        model's own table or any ``[rows, color_dim]`` table ``indices`` points into (the texture editors pass another
+        mesh's codes, ``editing/texture_neumesh/texture_neumesh.py:104-111``)."""
+        if (indices is not None and weights is not None and (nabla is not None or not self.enable_nablas_input)
+                and self._fused_ok(d, view_dirs, color_features, indices, weights)
+                and color_features.dim() == 2 and color_features.shape[1] == self._cfg["color_dim"]):
+            return self._fused_color(d, view_dirs, color_features, indices, weights, nabla)
         return self._forward_color(self.embed_fn_d(d), view_dirs, color_features, indices, weights, nabla)
+
+    def _fused_color(self, d, view_dirs, color_features, indices, weights, nabla):
+        lead = d.shape[:-1]
+        dev = d.device
+        ds = d.detach().reshape(-1).float().contiguous()
+        M = ds.shape[0]
+        rgb = torch.empty(M, 3, device=dev)
+        if M == 0:
+            return rgb.reshape(*lead, 3)
+        dirs = view_dirs.detach().reshape(-1, 3).float().contiguous()
+        idx = indices.detach().reshape(-1, 8).to(torch.int64).contiguous()
+        w = weights.detach().reshape(-1, 8).float().contiguous()
+        nab = nabla.detach().reshape(-1, 3).float().contiguous() if self.enable_nablas_input else None
+        own = (color_features.data_ptr() == self.color_features.data_ptr()
+               and color_features.shape == self.color_features.shape)
+        table = None if own else color_features.detach().float().contiguous()
+        field = self.packed_field()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().nmb_field_color(field, _lib.ptr(table), 0 if own else table.shape[0], _lib.ptr(ds),
+                                                  _lib.ptr(idx), _lib.ptr(w), _lib.ptr(nab), _lib.ptr(dirs), M,
+                                                  _lib.ptr(rgb), _lib.stream_ptr(dev)))
+        return rgb.reshape(*lead, 3)
 
     def forward_s(self):
         return torch.exp(self.ln_s * self.speed_factor)

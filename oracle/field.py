@@ -131,15 +131,16 @@ class FieldOracle:
         return sdf, nabla
 
     # -- colour branch ----------------------------------------------------------------------------------------
-    def _color_from(self, d_emb, view_dirs, idx, w, nabla):
-        """neumesh.py:239-260: input = [nabla?, PE_8(ds), PE_4(view), PE_2(ft)]."""
+    def _color_from(self, d_emb, view_dirs, idx, w, nabla, table=None):
+        """neumesh.py:239-260: input = [nabla?, PE_8(ds), PE_4(view), PE_2(ft)].  ``table`` = the ``color_features``
+        argument of ``forward_color`` (neumesh.py:156-168); default: the model's own codes."""
         c = self.cfg
         parts = []
         if self.enable_nablas_input:
             parts.append(nabla)
         parts.append(d_emb)
         parts.append(positional_encoding(view_dirs, c.multires_view))
-        ft = blend_rows(self.p["color_features"], idx, w)
+        ft = blend_rows(self.p["color_features"] if table is None else table.to(self.dtype), idx, w)
         parts.append(positional_encoding(ft, c.multires_ft))
         h = torch.cat(parts, dim=-1)
         hidden, (w_out, b_out) = self.color_layers()

@@ -101,7 +101,43 @@ def make_train_case(name, level, n_rays, seed):
     print("wrote", path, os.path.getsize(path), "bytes; loss", loss.item())
 
 
+def make_texture_case(name, seed):
+    """Point colours and a small render of the UNMODIFIED ``TextureEditableNeuMesh``
+    (``editing/texture_neumesh/texture_neumesh.py``) over reference ``NeuMesh`` models."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    ns = ref_harness.load()
+    case = helpers.texture_edit_case(seed)
+    main = ref_harness.build_reference_model(case["main_mesh"], case["cfg"], case["main_sd"])
+    refs = [ref_harness.build_reference_model(m, case["cfg"], sd) for m, sd in case["refs"]]
+    model = ns.texture_neumesh.TextureEditableNeuMesh(main, refs, case["masks"], case["codes"], T_r_m_list=case["T"])
+    model.eval()
+    torch.manual_seed(seed)
+    dirs = torch.nn.functional.normalize(torch.randn(500, 3), dim=-1)
+    radii = torch.cat([0.5 + 0.04 * torch.randn(350), 0.2 + 0.8 * torch.rand(150)])
+    xyz = dirs * radii[:, None]
+    view = torch.nn.functional.normalize(torch.randn(500, 3), dim=-1)
+    sdf, rgb = model.forward(xyz.clone(), view)
+    sdf_m, rgb_m = main.forward(xyz.clone(), view)
+    o, d = synth.frame_rays(10, 10, view=5)
+    kw = dict(calc_normal=False, white_bkgd=True, bounded_near_far=True)
+    with torch.no_grad():
+        r_rgb, r_depth, ex = ns.renderer.volume_render(o, d, model, detailed_output=False, rayschunk=4096, **kw)
+    changed = (rgb.detach() - rgb_m.detach()).abs().max(-1)[0] > 1e-6
+    out = dict(seed=np.int64(seed), digest_main=np.array(state_digest(case["main_sd"])),
+               digest_codes=np.array(state_digest({"codes": case["codes"], "masks": case["masks"].float()})),
+               xyz=xyz.numpy(), view_dirs=view.numpy(), sdf=sdf.detach().numpy(), rgb=rgb.detach().numpy(),
+               rgb_unedited=rgb_m.detach().numpy(), rays_o=o.numpy(), rays_d=d.numpy(), render_rgb=r_rgb.numpy(),
+               render_depth=r_depth.numpy())
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes; points recoloured by the edit:", int(changed.sum()), "of 500")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "texture":
+        make_texture_case("texture_edit_small", seed=40)
+        return
     cfg = synth.ModelConfig()
     make_case("scan63like_small", 4, 12, 12, cfg,
               dict(calc_normal=True, white_bkgd=True, bounded_near_far=True), seed=10)
@@ -109,6 +145,7 @@ def main():
     make_case("nonabla_unbounded", 3, 10, 10, cfg2,
               dict(calc_normal=False, white_bkgd=False, bounded_near_far=False), seed=20)
     make_train_case("train_step_small", 3, 48, seed=30)
+    make_texture_case("texture_edit_small", seed=40)
 
 
 if __name__ == "__main__":

@@ -70,6 +70,7 @@ def load():
         import models.frameworks.neumesh.neumesh as neumesh
         import utils.rend_util as rend_util
         import utils.train_util as train_util
+        import editing.texture_neumesh.texture_neumesh as texture_neumesh   # empty package __init__: no Open3D import
     finally:
         sys.path.remove(REF_ROOT)
 
@@ -90,7 +91,8 @@ def load():
             return self.vertices.shape[0]
 
     ns = types.SimpleNamespace(renderer=renderer, mesh_grid=mesh_grid, base=base, neumesh=neumesh,
-                               rend_util=rend_util, train_util=train_util, HarnessMeshGrid=HarnessMeshGrid)
+                               rend_util=rend_util, train_util=train_util, texture_neumesh=texture_neumesh,
+                               HarnessMeshGrid=HarnessMeshGrid)
     _loaded = ns
     return ns
 

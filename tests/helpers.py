@@ -91,3 +91,38 @@ def train_loss(rgb, depth, extras):
 TRAIN_KW = dict(calc_normal=True, white_bkgd=False, bounded_near_far=True, detailed_output=True, perturb=False)
 GRAD_KEYS = ["geometry_features", "color_features", "indicator_vector", "ln_s", "pts_linears.0.weight_v",
              "pts_linears.2.0.weight_g", "density_linear.weight_v", "views_linears.0.weight", "color_linear.0.bias"]
+
+
+def texture_edit_case(seed=40):
+    """Inputs of the texture-editing case: a main model, two reference models on other
+    meshes, two overlapping painted regions on the main mesh, transferred colour codes and main->reference rotations.
+    Deterministic in ``seed``; shared by ``tests/golden/make_golden.py`` and the tests."""
+    g = torch.Generator().manual_seed(seed)
+    cfg = synth.ModelConfig()
+    main_mesh = synth.icosphere_mesh(4, seed=seed)
+    main_sd = synth.make_state_dict(main_mesh, cfg, seed=seed + 1)
+    refs = []
+    for j, level in enumerate((3, 2)):
+        m = synth.icosphere_mesh(level, seed=seed + 10 + j)
+        refs.append((m, synth.make_state_dict(m, cfg, seed=seed + 20 + j)))
+    v = torch.from_numpy(main_mesh.vertices).float()
+    masks = torch.stack([v[:, 0] > 0.1, v[:, 2] > 0.25])                       # [2, V] bool, overlapping regions
+    codes = torch.randn(v.shape[0], cfg.color_dim, generator=g)                # transferred colour codes
+    rots = []
+    for _ in range(2):
+        q, _r = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64))
+        if torch.det(q) < 0:
+            q[:, 0] = -q[:, 0]
+        T = torch.eye(4)
+        T[:3, :3] = q.float()
+        T[:3, 3] = torch.randn(3, generator=g) * 0.1
+        rots.append(T)
+    return dict(cfg=cfg, main_mesh=main_mesh, main_sd=main_sd, refs=refs, masks=masks, codes=codes, T=rots)
+
+
+def texture_edit_oracle(case, dtype=torch.float32):
+    from oracle.texture import TextureEditOracle
+    main = oracle_field(case["main_mesh"], case["cfg"], case["main_sd"], dtype)
+    refs = [oracle_field(m, case["cfg"], sd, dtype) for m, sd in case["refs"]]
+    rot = torch.stack([T[:3, :3] for T in case["T"]])
+    return TextureEditOracle(main, refs, case["masks"], case["codes"], rot)
