@@ -18,7 +18,7 @@ PACK_KEYS = (("rgb", 3), ("depth_volume", 1), ("mask_volume", 1), ("normals_volu
 
 def shard_range(n_rays: int, rank: int, world: int):
     """Contiguous, balanced partition of [0, n_rays): sizes differ by at most one (kept for callers that need
-    contiguous blocks; rendering uses the interleaved ``shard_slice``)."""
+    contiguous blocks; rendering uses the block-cyclic ``shard_indices``)."""
     base, rem = divmod(n_rays, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
