@@ -561,6 +561,9 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
             "N_importance must be a multiple of N_upsample_iters");
   NMB_CHECK(!cfg->calc_normal || normals, "calc_normal needs a normals output");
   NMB_CHECK(workspace_bytes >= nmb_render_workspace_bytes(cfg, rays_per_chunk), "workspace too small");
+  NMB_CHECK(N < (int64_t(1) << 31), "at most 2^31 - 1 rays per call (32-bit ray permutation)");
+  NMB_CHECK(rays_per_chunk * (int64_t)(cfg->N_samples + cfg->N_importance) < (int64_t(1) << 31),
+            "rays_per_chunk x samples per ray must stay below 2^31 (32-bit live-sample offsets)");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (N <= 0) return 0;
   const int n_iters = cfg->N_upsample_iters;
