@@ -5,7 +5,8 @@ of the same fp32 parameters, for three operand schemes with fp32 accumulation -
 * ``3xTF32``   : a = hi + lo with tf32 (10-bit mantissa) parts, D = a_lo b_hi + a_hi b_lo + a_hi b_hi  (the current engine),
 * ``fp16x3``   : fp16 (10-bit mantissa) parts with exponent management so that ONE accumulator suffices:
                  B' = 2^8 W;  D' = a_hi B'_hi + (2^11 a_lo) (2^-11 B'_hi) + a_hi B'_lo;  z = 2^-8 D'
-                 - three f16-kind MMAs per K step run at twice the tf32 rate and read half the operand bytes.
+                 - three f16-kind MMAs per K step run at twice the tf32 rate and read half the operand bytes;
+* ``fp16x3p``  : the same without the 2^11 scaling of a_lo (B then needs only two images, exactly like 3xTF32).
 
 Products of two 11-bit significands are exact in fp32, so emulating each MMA as an fp32 matmul of the rounded operands
 differs from the tensor core only in accumulation order.  Usage: python tools/split_precision_study.py
@@ -50,6 +51,19 @@ def lin_fp16x3(a, w, b):
     return d * (1.0 / 256.0) + b
 
 
+def lin_fp16x3_plain(a, w, b):
+    """as fp16x3 but with the low part of A left unscaled (it may go subnormal: absolute error <= 2^-25 per element),
+    so B needs only its hi / lo images: D' = a_lo B'_hi + a_hi B'_lo + a_hi B'_hi"""
+    f16 = lambda t: t.half().float()   # noqa: E731
+    wp = w * 256.0
+    bh = f16(wp)
+    bl = f16(wp - bh)
+    ah = f16(a)
+    al = f16(a - ah)
+    d = (al @ bh.T + ah @ bl.T) + ah @ bh.T
+    return d * (1.0 / 256.0) + b
+
+
 def sdf_with(lin, f, x):
     c = f.cfg
     ds, idx, w = f.compute_distance(x)
@@ -72,7 +86,8 @@ def main():
         x, _ = helpers.sample_points(20000, seed=4)
         truth = f64.forward_density_only(x.double())
         print(f"vertex codes {dims[0]}-d, 20 000 points, |sdf| max {truth.abs().max():.2f}")
-        for name, lin in (("fp32", lin_fp32), ("3xTF32", lin_3xtf32), ("fp16x3", lin_fp16x3)):
+        for name, lin in (("fp32", lin_fp32), ("3xTF32", lin_3xtf32), ("fp16x3", lin_fp16x3),
+                          ("fp16x3p", lin_fp16x3_plain)):
             e = (sdf_with(lin, f32, x).double() - truth).abs()
             print(f"  {name:7s} max-abs {e.max():.3e}  mean {e.mean():.3e}  p99 {e.flatten().quantile(0.99):.3e}")
 
