@@ -175,7 +175,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "fp32"])
+    ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "fp32", "tcgen05_f16"],
+                    help="MLP engine; tcgen05_f16 (fp16x3 operands) is experimental and not validated on hardware yet")
     ap.add_argument("--chunk", type=int, default=0, help="rays per kernel chunk (0 = library default)")
     ap.add_argument("--ref-rays", type=int, default=1024, help="rays per step of the CPU reference arm")
     ap.add_argument("--cpu-rays", type=int, default=1536, help="rays of the cpu_baseline sample (0 = skip)")
@@ -435,7 +436,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None,
-            "dtype": "fp32 (MLPs: 3xTF32 tcgen05, fp32 accumulate)" if args.engine == "tcgen05" else "fp32",
+            "dtype": {"tcgen05": "fp32 (MLPs: 3xTF32 tcgen05, fp32 accumulate)",
+                      "tcgen05_f16": "fp32 (MLPs: fp16x3 tcgen05, fp32 accumulate; EXPERIMENTAL engine)"}.get(args.engine, "fp32"),
             "data": "synthetic", "config": {**workload_config(n_rays), "frames_per_step": fps,
                                             "parallelism": f"block-cyclic ray-shard x{world} + all_gather",
                                             "mlp_engine": args.engine,

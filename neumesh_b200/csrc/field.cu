@@ -131,7 +131,7 @@ static int pack_field(const nmb_field_desc* d, nmb_field* f, cudaStream_t stream
   NMB_CHECK(d->W == MLP_W, "fused kernels are specialised for W = 256");
   NMB_CHECK(d->geometry_dim >= FEAT && d->geometry_dim % FEAT == 0 && d->color_dim >= FEAT && d->color_dim % FEAT == 0,
             "fused kernels need vertex code widths that are multiples of 32");
-  NMB_CHECK(f->engine == 0 || (d->geometry_dim == FEAT && d->color_dim == FEAT),
+  NMB_CHECK(f->engine != 1 || (d->geometry_dim == FEAT && d->color_dim == FEAT),
             "the fp32 engine is specialised for 32-d vertex codes (use the tcgen05 engine)");
   NMB_CHECK(d->D_density >= 1 && d->D_density < MAX_LAYERS && d->D_color >= 1 && d->D_color < MAX_LAYERS,
             "unsupported MLP depth");
@@ -140,7 +140,7 @@ static int pack_field(const nmb_field_desc* d, nmb_field* f, cudaStream_t stream
   f->lay = make_layout(d);
   f->shell_valid = false;
   f->shell = ShellGrid{};
-  NMB_CHECK(f->engine == 0 || (f->lay.K0g <= 256 && f->lay.K0c <= 256),
+  NMB_CHECK(f->engine != 1 || (f->lay.K0g <= 256 && f->lay.K0c <= 256),
             "first-layer width exceeds the fp32 engine's 256-column tile");
   f->w1 = d->indicator_weight;
   f->s = d->s;
@@ -199,7 +199,7 @@ int nmb_field_create(const nmb_grid* g, const nmb_field_desc* desc, int mlp_engi
   if (!out) return 2;
   *out = nullptr;
   NMB_CHECK(g != nullptr && desc != nullptr, "null grid / descriptor");
-  NMB_CHECK(mlp_engine == 0 || mlp_engine == 1, "mlp_engine must be 0 (tcgen05) or 1 (fp32)");
+  NMB_CHECK(mlp_engine >= 0 && mlp_engine <= 2, "mlp_engine must be 0 (tcgen05 3xTF32), 1 (fp32) or 2 (tcgen05 fp16x3)");
   nmb_field* f = new nmb_field();
   f->grid = g;
   f->engine = mlp_engine;

@@ -82,10 +82,10 @@ int launch_geo_tc(const nmb_field* f, const FieldIn& in, int64_t P, float* sdf, 
 int launch_color_tc(const nmb_field* f, const FieldIn& in, int64_t P, float* rgb, cudaStream_t stream);
 
 inline int launch_geo(const nmb_field* f, const FieldIn& in, int64_t P, float* sdf, float* nabla, cudaStream_t s) {
-  return f->engine == 0 ? launch_geo_tc(f, in, P, sdf, nabla, s) : launch_geo_ffma(f, in, P, sdf, nabla, s);
+  return f->engine != 1 ? launch_geo_tc(f, in, P, sdf, nabla, s) : launch_geo_ffma(f, in, P, sdf, nabla, s);
 }
 inline int launch_color(const nmb_field* f, const FieldIn& in, int64_t P, float* rgb, cudaStream_t s) {
-  return f->engine == 0 ? launch_color_tc(f, in, P, rgb, s) : launch_color_ffma(f, in, P, rgb, s);
+  return f->engine != 1 ? launch_color_tc(f, in, P, rgb, s) : launch_color_ffma(f, in, P, rgb, s);
 }
 
 int permute_indicator(const nmb_grid* g, const float* indicator, float4* dst, cudaStream_t stream);

@@ -17,6 +17,8 @@
 // Operand layout (no-swizzle, K-major "interleave" canonical layout): a K-slab of 16 columns is stored as
 // [k/4][row][k%4] fp32, i.e. 8x16-byte core matrices with SBO = 128 B (next 8 rows) and LBO = rows*16 B (next 4 k).
 // Weights are pre-packed in exactly this image (hi slab then lo slab) so a slab is ONE contiguous 32 KB bulk copy.
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 #include <vector>
 
@@ -48,15 +50,25 @@ constexpr int WARP_BUILD = N_EPI / 32, WARP_MMA = (N_EPI + N_BUILD) / 32;
 constexpr int SIG_BUF = 64 * 16;           // floats per exp(100 z) exchange buffer (64 value rows x 16 columns)
 constexpr int CONST_FLOATS = (MAX_LAYERS + 3) * MLP_W;   // biases of every hidden layer + up to 3 output rows
 
-struct SmemLayout {
+// fp16x3 operand variant (mlp_engine = 2): the same slabs with fp16 hi / lo images - half the bytes, and a 16-column
+// slab is ONE kind::f16 K step (K = 16) instead of two tf32 ones.  Ring depths are kept equal to the tf32 variant.
+constexpr int A_HALF16 = ROWS * SLAB_K * 2;   // 4 KB
+constexpr int A_SLOT16 = 2 * A_HALF16;        // 8 KB
+constexpr int B_HALF16 = MLP_W * SLAB_K * 2;  // 8 KB
+constexpr int B_SLOT16 = 2 * B_HALF16;        // 16 KB
+constexpr float F16_W_SCALE = 256.f;          // weights are packed as 2^8 W (keeps their lo parts out of the subnormals)
+
+template <bool F16>
+struct SmemLayoutT {
   static constexpr int a_off = 0;
-  static constexpr int b_off = NA * A_SLOT;
-  static constexpr int sig_off = b_off + NB * B_SLOT;          // [group][parity] buffers
+  static constexpr int b_off = NA * (F16 ? A_SLOT16 : A_SLOT);
+  static constexpr int sig_off = b_off + NB * (F16 ? B_SLOT16 : B_SLOT);   // [group][parity] buffers
   static constexpr int part_off = sig_off + 4 * SIG_BUF * 4;   // last-layer partial sums: [3 helpers][3][128]
   static constexpr int const_off = part_off + 9 * ROWS * 4;    // biases + output weights
   static constexpr int bar_off = const_off + CONST_FLOATS * 4;
   static constexpr int total = bar_off + 256;
 };
+using SmemLayout = SmemLayoutT<false>;
 static_assert(SmemLayout::total <= 232448, "shared memory budget");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -154,6 +166,17 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
       : "memory");
 }
+// kind::f16 (A and B fp16, fp32 accumulate), same shape: a_format = b_format = 0 (F16)
+constexpr uint32_t IDESC_F16 = (1u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(IDESC_F16), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -249,6 +272,22 @@ __device__ __forceinline__ void store_a_half(char* a_slot, int r, int h, const f
   }
 }
 
+// fp16 variant of store_a_half: the 8 columns [8h, 8h+8) of row `r` are ONE 16-byte chunk ([k/8][row][k%8] halves);
+// hi = fp16(x), lo = fp16(x - hi) (lo may be subnormal: absolute error <= 2^-25, see tools/split_precision_study.py)
+__device__ __forceinline__ void store_a_half_f16(char* a_slot, int r, int h, const float (&v)[8]) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const __half2 hp = __floats2half2_rn(v[2 * c], v[2 * c + 1]);   // .x (low 16 bits) = even column
+    const float2 hf = __half22float2(hp);
+    const __half2 lp = __floats2half2_rn(v[2 * c] - hf.x, v[2 * c + 1] - hf.y);
+    hi[c] = *reinterpret_cast<const uint32_t*>(&hp);
+    lo[c] = *reinterpret_cast<const uint32_t*>(&lp);
+  }
+  *reinterpret_cast<uint4*>(a_slot + h * (ROWS * 16) + r * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(a_slot + A_HALF16 + h * (ROWS * 16) + r * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
 struct Params {
   FieldLayout lay;
   FieldIn in;
@@ -291,10 +330,14 @@ __device__ __forceinline__ void mbar_wait_bt(uint32_t bar, uint32_t parity, bool
 
 // MODE 0: geometry, 128 points / tile.  MODE 1: geometry + tangent rows (rows 64..127 carry d/d(ds) of rows 0..63).
 // MODE 2: colour, 128 points / tile.
-template <int MODE>
+// F16 = false: 3xTF32 operands (mlp_engine 0).  F16 = true: fp16x3 operands (mlp_engine 2, see A_HALF16 above).
+template <int MODE, bool F16 = false>
 __global__ void __cluster_dims__(tc::CLUSTER, 1, 1) __launch_bounds__(tc::THREADS, 1)
 mlp_tc_kernel(const tc::Params prm) {
   using namespace tc;
+  using SmemLayout = SmemLayoutT<F16>;
+  constexpr int A_HALF = F16 ? A_HALF16 : tc::A_HALF, A_SLOT = F16 ? A_SLOT16 : tc::A_SLOT;
+  constexpr int B_HALF = F16 ? B_HALF16 : tc::B_HALF, B_SLOT = F16 ? B_SLOT16 : tc::B_SLOT;
   extern __shared__ __align__(1024) char smem[];
   char* a_ring = smem + SmemLayout::a_off;
   char* b_ring = smem + SmemLayout::b_off;
@@ -387,7 +430,7 @@ mlp_tc_kernel(const tc::Params prm) {
           float v[8];
           tmem_ld_wait8(raw);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(raw[i]);
+          for (int i = 0; i < 8; ++i) v[i] = F16 ? __uint_as_float(raw[i]) * (1.0f / F16_W_SCALE) : __uint_as_float(raw[i]);
           if (j + 2 < N_CHUNK) tmem_ld8_issue(t_row + (uint32_t)((j + 2) * SLAB_K), raw);
           if (MODE == 2) {
 #pragma unroll
@@ -437,7 +480,8 @@ mlp_tc_kernel(const tc::Params prm) {
             const uint32_t qs = q + (uint32_t)j;
             const uint32_t slot = NA0 + qs % NA1;
             mbar_wait_t(bar(A_EMPTY + slot), ((qs / NA1) & 1u) ^ 1u, prof, t_aempty);
-            store_a_half(a_ring + slot * A_SLOT, r, hh, v);
+            if constexpr (F16) store_a_half_f16(a_ring + slot * A_SLOT, r, hh, v);
+            else store_a_half(a_ring + slot * A_SLOT, r, hh, v);
             fence_proxy_async();
             mbar_arrive(bar(A_FULL + slot));
           } else {
@@ -523,7 +567,8 @@ mlp_tc_kernel(const tc::Params prm) {
       auto emit = [&](const float (&v)[8]) {
         const uint32_t slot = q % NA0;
         mbar_wait(bar(A_EMPTY + slot), ((q / NA0) & 1u) ^ 1u);
-        store_a_half(a_ring + slot * A_SLOT, r, h, v);
+        if constexpr (F16) store_a_half_f16(a_ring + slot * A_SLOT, r, h, v);
+        else store_a_half(a_ring + slot * A_SLOT, r, h, v);
         fence_proxy_async();
         mbar_arrive(bar(A_FULL + slot));
         ++q;
@@ -644,16 +689,27 @@ mlp_tc_kernel(const tc::Params prm) {
             mbar_wait_bt(bar(B_FULL + sb), (q / NB) & 1u, prof, t_b);
             tc_fence_after();
             const uint32_t a_addr = a0 + sa * A_SLOT, b_addr = b0 + sb * B_SLOT;
+            if constexpr (F16) {
+              // one K = 16 step per slab: two 8-column chunks; chunk stride: A 128 rows * 16 B, B 256 rows * 16 B
+              const uint64_t a_hi = make_desc(a_addr, ROWS * 16, 128);
+              const uint64_t a_lo = make_desc(a_addr + A_HALF, ROWS * 16, 128);
+              const uint64_t b_hi = make_desc(b_addr, MLP_W * 16, 128);
+              const uint64_t b_lo = make_desc(b_addr + B_HALF, MLP_W * 16, 128);
+              mma_f16(d_tmem, a_lo, b_hi, j ? 1u : 0u);   // small terms first
+              mma_f16(d_tmem, a_hi, b_lo, 1u);
+              mma_f16(d_tmem, a_hi, b_hi, 1u);
+            } else {
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              // two 4-column chunks per K=8 step; chunk stride: A 128 rows * 16 B, B 256 rows * 16 B
-              const uint64_t a_hi = make_desc(a_addr + ks * 2 * (ROWS * 16), ROWS * 16, 128);
-              const uint64_t a_lo = make_desc(a_addr + A_HALF + ks * 2 * (ROWS * 16), ROWS * 16, 128);
-              const uint64_t b_hi = make_desc(b_addr + ks * 2 * (MLP_W * 16), MLP_W * 16, 128);
-              const uint64_t b_lo = make_desc(b_addr + B_HALF + ks * 2 * (MLP_W * 16), MLP_W * 16, 128);
-              mma_tf32(d_tmem, a_lo, b_hi, (j | ks) ? 1u : 0u);   // small terms first
-              mma_tf32(d_tmem, a_hi, b_lo, 1u);
-              mma_tf32(d_tmem, a_hi, b_hi, 1u);
+              for (int ks = 0; ks < 2; ++ks) {
+                // two 4-column chunks per K=8 step; chunk stride: A 128 rows * 16 B, B 256 rows * 16 B
+                const uint64_t a_hi = make_desc(a_addr + ks * 2 * (ROWS * 16), ROWS * 16, 128);
+                const uint64_t a_lo = make_desc(a_addr + A_HALF + ks * 2 * (ROWS * 16), ROWS * 16, 128);
+                const uint64_t b_hi = make_desc(b_addr + ks * 2 * (MLP_W * 16), MLP_W * 16, 128);
+                const uint64_t b_lo = make_desc(b_addr + B_HALF + ks * 2 * (MLP_W * 16), MLP_W * 16, 128);
+                mma_tf32(d_tmem, a_lo, b_hi, (j | ks) ? 1u : 0u);   // small terms first
+                mma_tf32(d_tmem, a_hi, b_lo, 1u);
+                mma_tf32(d_tmem, a_hi, b_hi, 1u);
+              }
             }
             mma_commit(bar(A_EMPTY + sa));
             mma_commit_mc(bar(B_EMPTY + sb), (uint16_t)((1u << CLUSTER) - 1u));
@@ -720,6 +776,24 @@ __global__ void pack_tc_kernel(const float* __restrict__ wt /*[K_src][256]*/, co
   base[tc::B_HALF / 4 + off] = lo;
 }
 
+// fp16x3 variant: per slab [hi | lo] x [k/8][256][k%8] halves of 2^8 W (hi = fp16(x), lo = fp16(x - hi))
+__global__ void pack_tc16_kernel(const float* __restrict__ wt /*[K_src][256]*/, const int32_t* __restrict__ kmap /*[K]*/,
+                                 int K, float* __restrict__ dst) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= (int64_t)K * MLP_W) return;
+  const int n = (int)(t % MLP_W);
+  const int k = (int)(t / MLP_W);
+  const int ksrc = kmap[k];
+  const float x = (ksrc >= 0 ? wt[(int64_t)ksrc * MLP_W + n] : 0.f) * tc::F16_W_SCALE;
+  const __half hi = __float2half_rn(x);
+  const __half lo = __float2half_rn(x - __half2float(hi));
+  const int slab = k / tc::SLAB_K, kk = k % tc::SLAB_K;
+  __half* base = reinterpret_cast<__half*>(dst + (int64_t)slab * (tc::B_SLOT16 / 4));
+  const int off = (kk / 8) * (MLP_W * 8) + n * 8 + (kk % 8);
+  base[off] = hi;
+  base[tc::B_HALF16 / 2 + off] = lo;
+}
+
 // TC first-layer column k -> FFMA first-layer column (both in "our" orders; see FieldLayout).
 // Builder half h (0/1) owns features F(g, h, i) = 8 g + 4 h + i (g < 4, i < 4) and columns [8h, 8h+8) of each slab:
 //   raw slab s (2):       col 8h + 4u + i  = feature F(2s + u, h, i)            (u < 2)
@@ -747,13 +821,14 @@ static std::vector<int32_t> tc_first_layer_map(const FieldLayout& L, bool color)
   return m;
 }
 
-static int pack_one(const MlpFfma& src, const FieldLayout& L, bool color, MlpTc* dst, cudaStream_t stream) {
+static int pack_one(const MlpFfma& src, const FieldLayout& L, bool color, bool f16, MlpTc* dst, cudaStream_t stream) {
   int64_t total = 0;
   dst->total_slabs = 0;
+  const int slot_floats = (f16 ? tc::B_SLOT16 : tc::B_SLOT) / 4;
   for (int l = 0; l < src.n_layers; ++l) {
     dst->n_slabs[l] = src.K[l] / tc::SLAB_K;
     dst->slab_off[l] = total;
-    total += (int64_t)dst->n_slabs[l] * (tc::B_SLOT / 4);
+    total += (int64_t)dst->n_slabs[l] * slot_floats;
     dst->total_slabs += dst->n_slabs[l];
   }
   NMB_CUDA_OK(dst->w.alloc(total));
@@ -770,8 +845,13 @@ static int pack_one(const MlpFfma& src, const FieldLayout& L, bool color, MlpTc*
     NMB_CUDA_OK(km.alloc((int64_t)kmap.size()));
     NMB_CUDA_OK(cudaMemcpyAsync(km.p, kmap.data(), kmap.size() * 4, cudaMemcpyHostToDevice, stream));
     const int64_t n = (int64_t)src.K[l] * MLP_W;
-    pack_tc_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(src.w.p + src.w_off[l], km.p, src.K[l],
-                                                                  dst->w.p + dst->slab_off[l]);
+    if (f16) {
+      pack_tc16_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(src.w.p + src.w_off[l], km.p, src.K[l],
+                                                                      dst->w.p + dst->slab_off[l]);
+    } else {
+      pack_tc_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(src.w.p + src.w_off[l], km.p, src.K[l],
+                                                                    dst->w.p + dst->slab_off[l]);
+    }
     NMB_LAUNCH_OK();
     NMB_CUDA_OK(cudaStreamSynchronize(stream));
   }
@@ -779,12 +859,13 @@ static int pack_one(const MlpFfma& src, const FieldLayout& L, bool color, MlpTc*
 }
 
 int pack_mlp_tc(const nmb_field_desc*, const FieldLayout& lay, nmb_field* f, cudaStream_t stream) {
-  int rc = pack_one(f->geo_f, lay, false, &f->geo_t, stream);
+  const bool f16 = f->engine == 2;   // geo_t / col_t hold the images of the engine the field was created for
+  int rc = pack_one(f->geo_f, lay, false, f16, &f->geo_t, stream);
   if (rc) return rc;
-  return pack_one(f->col_f, lay, true, &f->col_t, stream);
+  return pack_one(f->col_f, lay, true, f16, &f->col_t, stream);
 }
 
-template <int MODE>
+template <int MODE, bool F16>
 static int launch_tc(const nmb_field* f, const MlpFfma& fm, const MlpTc& tm, const FieldIn& in, int64_t P, float* out0,
                      float* out1, cudaStream_t stream) {
   if (P <= 0) return 0;
@@ -816,10 +897,10 @@ static int launch_tc(const nmb_field* f, const MlpFfma& fm, const MlpTc& tm, con
     prm.dbg = dbg_dev;
   }
   constexpr int PTS = (MODE == 1) ? 64 : 128;
-  const size_t smem = tc::SmemLayout::total;
+  const size_t smem = tc::SmemLayoutT<F16>::total;
   static DeviceOnce attr_once;
   NMB_CUDA_OK(attr_once.run([&] {
-    return cudaFuncSetAttribute(mlp_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return cudaFuncSetAttribute(mlp_tc_kernel<MODE, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }));
   const int64_t tiles = ceil_div(P, PTS);
   int64_t grid = tiles < (int64_t)sm_count() ? tiles : (int64_t)sm_count();
@@ -827,7 +908,7 @@ static int launch_tc(const nmb_field* f, const MlpFfma& fm, const MlpTc& tm, con
   if (grid > sm_count()) grid -= tc::CLUSTER;
   if (grid < tc::CLUSTER) grid = tc::CLUSTER;
   ProfScope prof(MODE == 2 ? PROF_COLOR : (MODE == 1 ? PROF_GEO_JVP : PROF_GEO), P, stream);
-  mlp_tc_kernel<MODE><<<(unsigned)grid, tc::THREADS, smem, stream>>>(prm);
+  mlp_tc_kernel<MODE, F16><<<(unsigned)grid, tc::THREADS, smem, stream>>>(prm);
   NMB_LAUNCH_OK();
   if (want_prof) {
     unsigned long long h[8];
@@ -845,12 +926,17 @@ static int launch_tc(const nmb_field* f, const MlpFfma& fm, const MlpTc& tm, con
 }
 
 int launch_geo_tc(const nmb_field* f, const FieldIn& in, int64_t P, float* sdf, float* nabla, cudaStream_t stream) {
-  if (nabla) return launch_tc<1>(f, f->geo_f, f->geo_t, in, P, sdf, nabla, stream);
-  return launch_tc<0>(f, f->geo_f, f->geo_t, in, P, sdf, nullptr, stream);
+  if (f->engine == 2) {
+    if (nabla) return launch_tc<1, true>(f, f->geo_f, f->geo_t, in, P, sdf, nabla, stream);
+    return launch_tc<0, true>(f, f->geo_f, f->geo_t, in, P, sdf, nullptr, stream);
+  }
+  if (nabla) return launch_tc<1, false>(f, f->geo_f, f->geo_t, in, P, sdf, nabla, stream);
+  return launch_tc<0, false>(f, f->geo_f, f->geo_t, in, P, sdf, nullptr, stream);
 }
 
 int launch_color_tc(const nmb_field* f, const FieldIn& in, int64_t P, float* rgb, cudaStream_t stream) {
-  return launch_tc<2>(f, f->col_f, f->col_t, in, P, rgb, nullptr, stream);
+  if (f->engine == 2) return launch_tc<2, true>(f, f->col_f, f->col_t, in, P, rgb, nullptr, stream);
+  return launch_tc<2, false>(f, f->col_f, f->col_t, in, P, rgb, nullptr, stream);
 }
 
 }  // namespace nmb

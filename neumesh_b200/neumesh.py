@@ -56,6 +56,12 @@ def _mlp_stack(make_linear, act, in_dim, width, depth):
     return nn.Sequential(*mods)
 
 
+# MLP engines of the CUDA library (nmb_field_create's mlp_engine).  "tcgen05_f16" (fp16x3 operands)
+# is EXPERIMENTAL: written against the numerical study in tools/split_precision_study.py, not yet validated on hardware,
+# never selected by default and not covered by the GPU tests.
+MLP_ENGINES = {"tcgen05": 0, "fp32": 1, "tcgen05_f16": 2}
+
+
 class NeuMesh(nn.Module):
     def __init__(self, mesh_grid, D_density: int, D_color: int, W: int, geometry_dim: int, color_dim: int,
                  multires_view: int, multires_d: int, multires_fg: int, multires_ft: int, enable_nablas_input: bool,
@@ -90,6 +96,8 @@ class NeuMesh(nn.Module):
         self._cfg = dict(D_density=D_density, D_color=D_color, W=W, geometry_dim=geometry_dim, color_dim=color_dim,
                          multires_view=multires_view, multires_d=multires_d, multires_fg=multires_fg,
                          multires_ft=multires_ft, input_view_dim=input_view_dim, input_d_dim=input_d_dim)
+        if mlp_engine not in MLP_ENGINES:
+            raise ValueError(f"mlp_engine must be one of {sorted(MLP_ENGINES)}")
         self.mlp_engine = mlp_engine
         self._field = None
         self._field_key = None
@@ -107,7 +115,7 @@ class NeuMesh(nn.Module):
 
     def fused_supported(self) -> bool:
         c = self._cfg
-        wide = self.mlp_engine == "tcgen05"      # the fp32 engine is specialised for 32-d codes
+        wide = self.mlp_engine != "fp32"         # the fp32 engine is specialised for 32-d codes
         dims_ok = all(d >= 32 and d % 32 == 0 and (wide or d == 32) for d in (c["geometry_dim"], c["color_dim"]))
         return (c["W"] == 256 and dims_ok and c["input_view_dim"] == 3
                 and c["input_d_dim"] == 1 and min(c["multires_d"], c["multires_fg"], c["multires_ft"],
@@ -153,7 +161,7 @@ class NeuMesh(nn.Module):
             d.geo_v[i], d.geo_g[i], d.geo_b[i] = dp(lin.weight_v), dp(lin.weight_g), dp(lin.bias)
         for i, lin in enumerate(self._col_linears()):
             d.col_w[i], d.col_b[i] = dp(lin.weight), dp(lin.bias)
-        engine = {"tcgen05": 0, "fp32": 1}[self.mlp_engine]
+        engine = MLP_ENGINES[self.mlp_engine]
         with torch.cuda.device(dev):
             if self._field is not None and self._field_key is not None and self._field_key[:3] == key[:3]:
                 _lib.check(_lib.lib().nmb_field_update(self._field, C.byref(d), _lib.stream_ptr(dev)))
