@@ -56,6 +56,7 @@ struct nmb_field {
   mutable nmb::DevBuf<float4> node_normals;   // per octree node: mean indicator vector, max deviation
   mutable bool shell_valid = false;
   mutable nmb::ShellGrid shell{};
+  mutable std::mutex shell_mu;                // serialises the lazy build when several host threads share the field
 };
 
 namespace nmb {

@@ -179,6 +179,7 @@ shell_certify_kernel(const float4* __restrict__ nodes, const float4* __restrict_
 }
 
 int ensure_shell_grid(const nmb_field* f, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(f->shell_mu);
   if (f->shell_valid) return 0;
   const nmb_grid* g = f->grid;
   f->shell = ShellGrid{};
@@ -224,6 +225,8 @@ int ensure_shell_grid(const nmb_field* f, cudaStream_t stream) {
   sg.cy = root_sphere.y;
   sg.cz = root_sphere.z;
   sg.far_r = root_sphere.w + (float)rho_safe + 1e-3f;   // beyond this every vertex is farther than rho_safe
+  // one-off build: complete it before publishing, so that renders on OTHER streams may use the cells right away
+  NMB_CUDA_OK(cudaStreamSynchronize(stream));
   f->shell = sg;
   return 0;
 }
