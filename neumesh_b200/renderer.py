@@ -24,7 +24,8 @@ DEFAULT_FUSED_CHUNK = 1 << 20  # rays per kernel chunk on the fused path (scratc
 
 
 def _workspace(device, nbytes):
-    key = (device.type, device.index)
+    # one scratch per (device, stream): renders issued on different streams of one device never share scratch
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _WORKSPACES.get(key)
     if ws is None or ws.numel() < nbytes:
         _WORKSPACES.pop(key, None)
@@ -35,12 +36,13 @@ def _workspace(device, nbytes):
 
 def release_workspace(device: Optional[torch.device] = None) -> None:
     """Drop the cached ``nmb_render`` scratch of ``device`` (all devices when None).  The fused path keeps one scratch
-    tensor per device sized for the largest chunk rendered so far (~21 GB at the default 2^20-ray chunk)."""
+    tensor per device and stream sized for the largest chunk rendered so far (~21 GB at the default 2^20-ray chunk)."""
     if device is None:
         _WORKSPACES.clear()
     else:
         device = torch.device(device)
-        _WORKSPACES.pop((device.type, device.index), None)
+        for key in [k for k in _WORKSPACES if k[:2] == (device.type, device.index)]:
+            _WORKSPACES.pop(key, None)
 
 
 def fused_eligible(model, rays_o, *, batched, perturb, random_color_direction, use_view_dirs, N_samples, N_importance,
