@@ -14,7 +14,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import neumesh_b200 as nb  # noqa: E402
 from neumesh_b200 import synth  # noqa: E402
-from neumesh_b200.renderer import get_rays  # noqa: E402
+from neumesh_b200.renderer import get_rays, pack_bgr8  # noqa: E402
 
 
 def main():
@@ -41,9 +41,9 @@ def main():
         with torch.no_grad():
             rgb, depth, extras = renderer(rays_o[None], rays_d[None], batched=True, calc_normal=True, white_bkgd=True,
                                           detailed_output=False, perturb=False)
-        img = (rgb[0].reshape(H, W, 3).clamp(0, 1).cpu().numpy() * 255).astype(np.uint8)
+        img_bgr = pack_bgr8(rgb[0]).reshape(H, W, 3).cpu().numpy()   # clamp, x255, uint8, BGR on the device
         nrm = ((extras["normals_volume"][0].reshape(H, W, 3).cpu().numpy() * 0.5 + 0.5).clip(0, 1) * 255).astype(np.uint8)
-        cv2.imwrite(os.path.join(args.out, f"rgb_{i:03d}.png"), img[..., ::-1])
+        cv2.imwrite(os.path.join(args.out, f"rgb_{i:03d}.png"), img_bgr)
         cv2.imwrite(os.path.join(args.out, f"normal_{i:03d}.png"), nrm[..., ::-1])
         print(f"view {i}: mean acc {extras['mask_volume'].mean().item():.3f}")
 
