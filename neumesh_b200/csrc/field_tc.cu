@@ -51,24 +51,27 @@ constexpr int SIG_BUF = 64 * 16;           // floats per exp(100 z) exchange buf
 constexpr int CONST_FLOATS = (MAX_LAYERS + 3) * MLP_W;   // biases of every hidden layer + up to 3 output rows
 
 // fp16x3 operand variant (mlp_engine = 2): the same slabs with fp16 hi / lo images - half the bytes, and a 16-column
-// slab is ONE kind::f16 K step (K = 16) instead of two tf32 ones.  Ring depths are kept equal to the tf32 variant.
+// slab is ONE kind::f16 K step (K = 16) instead of two tf32 ones.  The halved slots buy rings twice as deep.
 constexpr int A_HALF16 = ROWS * SLAB_K * 2;   // 4 KB
 constexpr int A_SLOT16 = 2 * A_HALF16;        // 8 KB
 constexpr int B_HALF16 = MLP_W * SLAB_K * 2;  // 8 KB
 constexpr int B_SLOT16 = 2 * B_HALF16;        // 16 KB
 constexpr float F16_W_SCALE = 256.f;          // weights are packed as 2^8 W (keeps their lo parts out of the subnormals)
+constexpr int NA0_16 = 4, NA1_16 = 8, NA_16 = NA0_16 + NA1_16, NB_16 = 6;
 
 template <bool F16>
 struct SmemLayoutT {
   static constexpr int a_off = 0;
-  static constexpr int b_off = NA * (F16 ? A_SLOT16 : A_SLOT);
-  static constexpr int sig_off = b_off + NB * (F16 ? B_SLOT16 : B_SLOT);   // [group][parity] buffers
+  static constexpr int b_off = F16 ? NA_16 * A_SLOT16 : NA * A_SLOT;
+  static constexpr int sig_off = b_off + (F16 ? NB_16 * B_SLOT16 : NB * B_SLOT);   // [group][parity] buffers
   static constexpr int part_off = sig_off + 4 * SIG_BUF * 4;   // last-layer partial sums: [3 helpers][3][128]
   static constexpr int const_off = part_off + 9 * ROWS * 4;    // biases + output weights
   static constexpr int bar_off = const_off + CONST_FLOATS * 4;
-  static constexpr int total = bar_off + 256;
+  static constexpr int total = bar_off + (F16 ? 512 : 256);   // 2 (NA + NB) + 4 mbarriers + the TMEM base address
 };
 using SmemLayout = SmemLayoutT<false>;
+static_assert(SmemLayoutT<true>::total <= 232448, "shared memory budget (fp16 variant)");
+static_assert((2 * (NA_16 + NB_16) + 4) * 8 + 4 <= 512 && (2 * (NA + NB) + 4) * 8 + 4 <= 256, "mbarrier block");
 static_assert(SmemLayout::total <= 232448, "shared memory budget");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -338,6 +341,7 @@ mlp_tc_kernel(const tc::Params prm) {
   using SmemLayout = SmemLayoutT<F16>;
   constexpr int A_HALF = F16 ? A_HALF16 : tc::A_HALF, A_SLOT = F16 ? A_SLOT16 : tc::A_SLOT;
   constexpr int B_HALF = F16 ? B_HALF16 : tc::B_HALF, B_SLOT = F16 ? B_SLOT16 : tc::B_SLOT;
+  constexpr int NA0 = F16 ? NA0_16 : tc::NA0, NA1 = F16 ? NA1_16 : tc::NA1, NA = NA0 + NA1, NB = F16 ? NB_16 : tc::NB;
   extern __shared__ __align__(1024) char smem[];
   char* a_ring = smem + SmemLayout::a_off;
   char* b_ring = smem + SmemLayout::b_off;
