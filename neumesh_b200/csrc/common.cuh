@@ -59,18 +59,23 @@ struct StreamBuf {
   T* as() const { return static_cast<T*>(p); }
 };
 
-// Run `f` (-> cudaError_t) once per CUDA device of this process (kernel attributes are per device); thread-safe.
+// Run `f` (-> cudaError_t) until it has succeeded once per CUDA device of this process (kernel attributes are per
+// device); thread-safe.
 constexpr int NMB_MAX_DEVICES = 64;
 struct DeviceOnce {
-  std::once_flag flags[NMB_MAX_DEVICES];
+  std::mutex mu;
+  bool done[NMB_MAX_DEVICES] = {};
   template <typename F>
   cudaError_t run(F&& f) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    cudaError_t rc = cudaSuccess;
-    std::call_once(flags[dev % NMB_MAX_DEVICES], [&] { rc = f(); });
-    return rc;
+    std::lock_guard<std::mutex> lock(mu);
+    bool& d = done[dev % NMB_MAX_DEVICES];
+    if (d) return cudaSuccess;
+    e = f();               // a failed attempt is reported AND retried by the next call (the flag is only set on success)
+    if (e == cudaSuccess) d = true;
+    return e;
   }
 };
 

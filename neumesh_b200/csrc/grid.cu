@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "grid.cuh"
+#include "knn_coop.cuh"
 #include "knn_walk.cuh"
 
 namespace nmb {
@@ -239,6 +240,29 @@ __global__ void lvl_boxes_kernel(int32_t first_node, int32_t n_nodes, const int3
   nodes[NODE_F4 * n + 3] = make_float4(ux, uy, uz, th);
 }
 
+
+// Directory tables of the cooperative walk (knn_coop.cuh).  One thread per octree node of depth `depth`: a node AT a
+// directory level fills its own cell; a LEAF above a directory level fills every cell it covers at that level.
+__global__ void dir_fill_kernel(int32_t first_node, int32_t n_nodes, int depth, int L, const uint32_t* __restrict__ code,
+                                const int32_t* __restrict__ nbegin, const int32_t* __restrict__ nfirst, int lmin, int lmax,
+                                const int32_t* __restrict__ dir_off /*[lmax - lmin + 1] on device*/,
+                                int32_t* __restrict__ dir) {
+  const int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_nodes) return;
+  const int32_t n = first_node + t;
+  const uint32_t prefix = depth == 0 ? 0u : (code[nbegin[n]] >> (3 * (L - depth)));
+  const bool leaf = nfirst[n] < 0;
+  for (int l = max(lmin, depth); l <= lmax; ++l) {
+    if (l == depth) {
+      dir[dir_off[l - lmin] + prefix] = n;
+    } else if (leaf) {
+      const int sh = 3 * (l - depth);
+      const uint32_t b = prefix << sh, e = (prefix + 1u) << sh;
+      for (uint32_t c = b; c < e; ++c) dir[dir_off[l - lmin] + c] = n;
+    }
+  }
+}
+
 static int build_grid(const float* vertices, int64_t V, cudaStream_t stream, nmb_grid* g) {
   NMB_CHECK(V >= KNN_K, "mesh needs at least 8 vertices");
   NMB_CHECK(V < (int64_t(1) << 30), "too many vertices");
@@ -370,8 +394,50 @@ static int build_grid(const float* vertices, int64_t V, cudaStream_t stream, nmb
                                                                                nlast.p, g->pts.p, g->nodes.p);
     NMB_LAUNCH_OK();
   }
+  // directory tables: levels [3, min(L - 1, 7)] (finer cells than the vertex spacing buy nothing)
+  g->dir_lmin = 3;
+  g->dir_lmax = std::min(L - 1, 7);
+  if (getenv("NMB_KNN_DIR_MAX")) g->dir_lmax = std::min(g->dir_lmax, atoi(getenv("NMB_KNN_DIR_MAX")));
+  if (g->dir_lmax >= g->dir_lmin) {
+    int64_t total = 0;
+    int32_t offs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int l = g->dir_lmin; l <= g->dir_lmax; ++l) {
+      offs[l - g->dir_lmin] = (int32_t)total;
+      g->dir_off[l - g->dir_lmin] = (int32_t)total;
+      total += int64_t(1) << (3 * l);
+    }
+    NMB_CUDA_OK(g->dir.alloc(total));
+    NMB_CUDA_OK(cudaMemsetAsync(g->dir.p, 0xff, sizeof(int32_t) * total, stream));
+    StreamBuf offs_dev;
+    NMB_CUDA_OK(offs_dev.alloc(sizeof(offs), stream));
+    NMB_CUDA_OK(cudaMemcpyAsync(offs_dev.p, offs, sizeof(offs), cudaMemcpyHostToDevice, stream));
+    for (int dpt = 0; dpt + 1 < (int)lvl_off.size() && dpt <= g->dir_lmax; ++dpt) {
+      const int32_t first = lvl_off[dpt], cnt = lvl_off[dpt + 1] - lvl_off[dpt];
+      if (cnt <= 0) continue;
+      dir_fill_kernel<<<(unsigned)ceil_div(cnt, threads), threads, 0, stream>>>(
+          first, cnt, dpt, L, code.p, nbegin.p, nfirst.p, g->dir_lmin, g->dir_lmax, offs_dev.as<int32_t>(), g->dir.p);
+      NMB_LAUNCH_OK();
+    }
+    NMB_CUDA_OK(cudaStreamSynchronize(stream));   // `offs` is a stack array
+  }
   NMB_CUDA_OK(cudaStreamSynchronize(stream));
   return 0;
+}
+
+GridView make_view(const nmb_grid* g) {
+  GridView v{};
+  v.nodes = g->nodes.p;
+  v.pts = g->pts.p;
+  static const bool no_dir = getenv("NMB_KNN_NO_DIR") != nullptr;
+  v.dir = (g->dir_lmax >= g->dir_lmin && !no_dir) ? g->dir.p : nullptr;
+  v.dir_lmin = g->dir_lmin;
+  v.dir_lmax = v.dir ? g->dir_lmax : g->dir_lmin - 1;
+  v.bmin[0] = g->bmin[0];
+  v.bmin[1] = g->bmin[1];
+  v.bmin[2] = g->bmin[2];
+  v.inv_cell = g->inv_cell;
+  v.levels = g->levels;
+  return v;
 }
 
 __device__ __forceinline__ void load_query(const PointSrc& src, int64_t p, float& qx, float& qy, float& qz) {
@@ -538,10 +604,208 @@ knn_lists_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pt
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// group-cooperative kernels (knn_coop.cuh): 8 lanes per query chain, 16 chains per 128-thread block
+// ------------------------------------------------------------------------------------------------------------
+static bool knn_legacy() {
+  static const bool v = getenv("NMB_KNN_LEGACY") != nullptr;   // thread-per-query kernels (verification / A-B timing)
+  return v;
+}
+
+#define NMB_COOP_PROLOGUE()                                                                    \
+  __shared__ uint32_t stack_mem[coop::GROUPS_PER_BLOCK * coop::STACK_WORDS];                   \
+  const coop::Lane ln = coop::make_lane();                                                     \
+  uint32_t* stk = stack_mem + (threadIdx.x / coop::G) * coop::STACK_WORDS;                     \
+  const int32_t root_link = __float_as_int(__ldg(&gv.nodes[0]).w);                             \
+  const int32_t root_cnt = __float_as_int(__ldg(&gv.nodes[1]).w);                              \
+  const int64_t chain = blockIdx.x * (int64_t)coop::GROUPS_PER_BLOCK + threadIdx.x / coop::G;
+
+// explicit points or ray samples in any order: one cold query per group
+template <int MINB>
+__global__ void __launch_bounds__(coop::BLOCK, MINB)
+knn_points_coop_kernel(GridView gv, const float4* __restrict__ indicator, float w1, PointSrc src, int64_t P, KnnOut out) {
+  NMB_COOP_PROLOGUE()
+  if (chain >= P) return;
+  float qx, qy, qz;
+  load_query(src, chain, qx, qy, qz);
+  float d;
+  int32_t ix;
+  coop::query(gv, ln, stk, root_link, root_cnt, indicator, w1, qx, qy, qz, false, d, ix, out, chain);
+}
+
+// ray-ordered: chain t = g * R + r walks samples [g * seg, (g + 1) * seg) of ray r in depth order, every query
+// warm-started with the previous sample's neighbours; the 4 chains of a warp are 4 neighbouring rays
+template <int MINB>
+__global__ void __launch_bounds__(coop::BLOCK, MINB)
+knn_rays_coop_kernel(GridView gv, const float4* __restrict__ indicator, float w1, PointSrc src, int S, int seg, KnnOut out) {
+  NMB_COOP_PROLOGUE()
+  const int64_t r = chain % src.R;
+  const int s_begin = (int)(chain / src.R) * seg;
+  if (s_begin >= S) return;
+  const int s_end = min(s_begin + seg, S);
+  const float ox = src.rays_o[r * 3 + 0], oy = src.rays_o[r * 3 + 1], oz = src.rays_o[r * 3 + 2];
+  const float dx = src.rays_d[r * 3 + 0], dy = src.rays_d[r * 3 + 1], dz = src.rays_d[r * 3 + 2];
+  float d;
+  int32_t ix;
+  for (int s = s_begin; s < s_end; ++s) {
+    const int64_t p = (int64_t)s * src.R + r;
+    const float z = src.z[p];
+    const float qx = __fadd_rn(ox, __fmul_rn(z, dx));
+    const float qy = __fadd_rn(oy, __fmul_rn(z, dy));
+    const float qz = __fadd_rn(oz, __fmul_rn(z, dz));
+    coop::query(gv, ln, stk, root_link, root_cnt, indicator, w1, qx, qy, qz, s != s_begin, d, ix, out, p);
+  }
+}
+
+// per-ray lists of explicit points (the compacted live samples of nmb_render): chain t = g * R + r handles entries
+// [g * seg, (g + 1) * seg) of ray r's list
+template <int MINB>
+__global__ void __launch_bounds__(coop::BLOCK, MINB)
+knn_lists_coop_kernel(GridView gv, const float4* __restrict__ indicator, float w1, const float* __restrict__ xyz,
+                      const int32_t* __restrict__ off, const int32_t* __restrict__ cnt, int64_t R, int seg, int max_seg,
+                      KnnOut out) {
+  NMB_COOP_PROLOGUE()
+  const int64_t r = chain % R;
+  const int gseg = (int)(chain / R);
+  if (gseg >= max_seg) return;
+  const int64_t b = off[r];
+  const int j_begin = gseg * seg;
+  const int n = min(cnt[r], j_begin + seg);
+  float d;
+  int32_t ix;
+  for (int j = j_begin; j < n; ++j) {
+    const int64_t p = b + j;
+    const float qx = xyz[p * 3], qy = xyz[p * 3 + 1], qz = xyz[p * 3 + 2];
+    coop::query(gv, ln, stk, root_link, root_cnt, indicator, w1, qx, qy, qz, j != j_begin, d, ix, out, p);
+  }
+}
+
+// bounded near / far, every sample evaluated (small launches): one cold query per group
+template <int MINB>
+__global__ void __launch_bounds__(coop::BLOCK, MINB)
+bound_scan_coop_kernel(GridView gv, const float4* __restrict__ indicator, float w1, const float* __restrict__ rays_o,
+                       const float* __restrict__ dirs, const float* __restrict__ near, const float* __restrict__ far,
+                       int64_t R, int n_grid, float thresh, int32_t* __restrict__ bnear, int32_t* __restrict__ bfar) {
+  NMB_COOP_PROLOGUE()
+  if (chain >= R * n_grid) return;
+  const int64_t r = chain % R;
+  const int s = (int)(chain / R);
+  const float t = linspace01(s, n_grid);
+  const float dep = __fadd_rn(__fmul_rn(near[r], __fsub_rn(1.0f, t)), __fmul_rn(far[r], t));  // renderer.py:81
+  const float qx = __fadd_rn(rays_o[r * 3 + 0], __fmul_rn(dep, dirs[r * 3 + 0]));
+  const float qy = __fadd_rn(rays_o[r * 3 + 1], __fmul_rn(dep, dirs[r * 3 + 1]));
+  const float qz = __fadd_rn(rays_o[r * 3 + 2], __fmul_rn(dep, dirs[r * 3 + 2]));
+  float d;
+  int32_t ix;
+  const float ds = coop::query(gv, ln, stk, root_link, root_cnt, indicator, w1, qx, qy, qz, false, d, ix, KnnOut{}, 0);
+  if (ds < thresh && ln.gl == 0) {
+    atomicMin(&bnear[r], __float_as_int(dep));
+    atomicMax(&bfar[r], __float_as_int(dep));
+  }
+}
+
+// ray-ordered bounded near / far with early exit and the shell certificate (same logic as bound_rays_kernel below):
+// chain t = g * R + r scans samples [g * BOUND_SEG, (g + 1) * BOUND_SEG) of ray r from the front to its first hit and
+// from the back to its last hit
+constexpr int BOUND_SEG_COOP = 32;
+template <int MINB>
+__global__ void __launch_bounds__(coop::BLOCK, MINB)
+bound_rays_coop_kernel(GridView gv, const float4* __restrict__ indicator, float w1, const float* __restrict__ rays_o,
+                       const float* __restrict__ dirs, const float* __restrict__ near, const float* __restrict__ far,
+                       int64_t R, int n_grid, float thresh, int32_t* __restrict__ bnear, int32_t* __restrict__ bfar,
+                       ShellGrid shell) {
+  NMB_COOP_PROLOGUE()
+  const int64_t r = chain % R;
+  const int s_begin = (int)(chain / R) * BOUND_SEG_COOP;
+  if (s_begin >= n_grid) return;
+  const int s_end = min(s_begin + BOUND_SEG_COOP, n_grid);
+  const float ox = rays_o[r * 3 + 0], oy = rays_o[r * 3 + 1], oz = rays_o[r * 3 + 2];
+  const float dx = dirs[r * 3 + 0], dy = dirs[r * 3 + 1], dz = dirs[r * 3 + 2];
+  const float nr = near[r], fr = far[r];
+  float d;
+  int32_t ix;
+  bool have_prev = false;   // the lanes hold the neighbours of some earlier sample of this ray (valid warm start)
+  // mesh distance at sample s, or +inf / -inf when the sample lies in a cell certified outside / inside the shell
+  auto ds_at = [&](int s, float& depth) {
+    const float tt = linspace01(s, n_grid);
+    depth = __fadd_rn(__fmul_rn(nr, __fsub_rn(1.0f, tt)), __fmul_rn(fr, tt));  // renderer.py:81
+    const float qx = __fadd_rn(ox, __fmul_rn(depth, dx));
+    const float qy = __fadd_rn(oy, __fmul_rn(depth, dy));
+    const float qz = __fadd_rn(oz, __fmul_rn(depth, dz));
+    if (shell.cells) {
+      const float sc = 0.5f * (float)shell.G / shell.B;
+      const float fx = (qx + shell.B) * sc, fy = (qy + shell.B) * sc, fz = (qz + shell.B) * sc;
+      if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)shell.G && fy < (float)shell.G && fz < (float)shell.G) {
+        const int64_t cell = ((int64_t)(int)fz * shell.G + (int)fy) * shell.G + (int)fx;
+        const uint8_t code = __ldg(shell.cells + cell);
+        if (code == 1) return CUDART_INF_F;    // proven outside the shell: mask false
+        if (code == 2) return -CUDART_INF_F;   // proven inside the shell: mask true (only the depth matters)
+      } else {
+        const float ex = qx - shell.cx, ey = qy - shell.cy, ez = qz - shell.cz;
+        if (ex * ex + ey * ey + ez * ez >= shell.far_r * shell.far_r) return CUDART_INF_F;
+      }
+    }
+    const bool warm = have_prev;
+    have_prev = true;
+    return coop::query(gv, ln, stk, root_link, root_cnt, indicator, w1, qx, qy, qz, warm, d, ix, KnnOut{}, 0);
+  };
+  int first = -1;
+  float depth = 0.f;
+  for (int s = s_begin; s < s_end; ++s) {
+    if (ds_at(s, depth) < thresh) {
+      first = s;
+      if (ln.gl == 0) atomicMin(&bnear[r], __float_as_int(depth));   // depths are >= 0: bit patterns order like values
+      break;
+    }
+  }
+  if (first < 0) return;  // no hit in this segment
+  for (int s = s_end - 1; s >= first; --s) {
+    if (s == first) {   // known to be a hit: the loop always terminates with a far candidate
+      if (ln.gl == 0) atomicMax(&bfar[r], __float_as_int(depth));
+      break;
+    }
+    float dd;
+    if (ds_at(s, dd) < thresh) {
+      if (ln.gl == 0) atomicMax(&bfar[r], __float_as_int(dd));
+      break;
+    }
+  }
+}
+
+static int coop_minb() {
+  static const int v = getenv("NMB_KNN_MINB") ? atoi(getenv("NMB_KNN_MINB")) : 8;
+  return v;
+}
+// launch helper: picks the instantiation for the tuned number of resident blocks per SM
+#define NMB_COOP_LAUNCH(kernel, nblocks, stream, ...)                                                      \
+  do {                                                                                                     \
+    const int mb_ = coop_minb();                                                                           \
+    if (mb_ >= 12) kernel<12><<<(unsigned)(nblocks), coop::BLOCK, 0, stream>>>(__VA_ARGS__);              \
+    else if (mb_ >= 10) kernel<10><<<(unsigned)(nblocks), coop::BLOCK, 0, stream>>>(__VA_ARGS__);         \
+    else if (mb_ >= 8) kernel<8><<<(unsigned)(nblocks), coop::BLOCK, 0, stream>>>(__VA_ARGS__);           \
+    else kernel<6><<<(unsigned)(nblocks), coop::BLOCK, 0, stream>>>(__VA_ARGS__);                         \
+  } while (0)
+
+// chains resident on the device at once (for sizing segments)
+static int64_t coop_resident_chains() { return (int64_t)sm_count() * coop_minb() * coop::GROUPS_PER_BLOCK; }
+constexpr int64_t COOP_RAY_KERNEL_MIN_RAYS = 2048;   // below this the per-point kernels expose more parallelism
+
 int launch_knn_lists(const nmb_grid* g, const float4* indicator_sorted, float w1, const float* xyz, const int32_t* off,
                      const int32_t* cnt, int64_t R, int64_t M, int max_list, KnnOut out, cudaStream_t stream) {
   if (M <= 0 || R <= 0) return 0;
   ProfScope prof(PROF_KNN_LIST, M, stream);
+  if (!knn_legacy()) {
+    // segments: enough chains for ~4 waves, at least 8 entries each
+    int64_t nseg = ceil_div(4 * coop_resident_chains(), R);
+    nseg = std::max<int64_t>(1, std::min<int64_t>(nseg, ceil_div(max_list, 8)));
+    const int seg = (int)ceil_div(max_list, nseg);
+    const int max_seg = (int)ceil_div(max_list, seg);
+    NMB_COOP_LAUNCH(knn_lists_coop_kernel, ceil_div(R * max_seg, coop::GROUPS_PER_BLOCK), stream, make_view(g),
+                    indicator_sorted, w1, xyz, off, cnt, R, seg, max_seg, out);
+    NMB_LAUNCH_OK();
+    return 0;
+  }
   const int seg = 16;
   const int max_seg = (int)ceil_div(max_list, seg);
   knn_lists_kernel<<<(unsigned)ceil_div(R * max_seg, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1,
@@ -556,6 +820,22 @@ int launch_knn_distance(const nmb_grid* g, const float4* indicator_sorted, float
                         KnnOut out, cudaStream_t stream) {
   if (P <= 0) return 0;
   ProfScope prof(PROF_KNN, P, stream);
+  if (!knn_legacy()) {
+    if (!src.xyz && src.R >= COOP_RAY_KERNEL_MIN_RAYS && P % src.R == 0) {
+      const int S = (int)(P / src.R);
+      int64_t nseg = ceil_div(4 * coop_resident_chains(), src.R);
+      nseg = std::max<int64_t>(1, std::min<int64_t>(nseg, ceil_div(S, 8)));
+      const int seg = (int)ceil_div(S, nseg);
+      nseg = ceil_div(S, seg);
+      NMB_COOP_LAUNCH(knn_rays_coop_kernel, ceil_div(src.R * nseg, coop::GROUPS_PER_BLOCK), stream, make_view(g),
+                      indicator_sorted, w1, src, S, seg, out);
+    } else {
+      NMB_COOP_LAUNCH(knn_points_coop_kernel, ceil_div(P, coop::GROUPS_PER_BLOCK), stream, make_view(g),
+                      indicator_sorted, w1, src, P, out);
+    }
+    NMB_LAUNCH_OK();
+    return 0;
+  }
   if (!src.xyz && src.R >= RAY_KERNEL_MIN_RAYS && P % src.R == 0) {
     const int S = (int)(P / src.R);
     // segments per ray: enough threads to fill the GPU (~2 waves of 1024 threads per SM), at least 8 samples each
@@ -693,6 +973,18 @@ int launch_bound_scan(const nmb_grid* g, const float4* indicator, float w1, cons
   const int64_t n = R * n_grid;
   if (n <= 0) return 0;
   ProfScope prof(PROF_BOUND, n, stream);
+  if (!knn_legacy()) {
+    if (R >= COOP_RAY_KERNEL_MIN_RAYS) {
+      const int64_t nseg = ceil_div(n_grid, BOUND_SEG_COOP);
+      NMB_COOP_LAUNCH(bound_rays_coop_kernel, ceil_div(R * nseg, coop::GROUPS_PER_BLOCK), stream, make_view(g), indicator,
+                      w1, rays_o, dirs, near, far, R, n_grid, thresh, bnear, bfar, (thresh == 0.1f) ? shell : ShellGrid{});
+    } else {
+      NMB_COOP_LAUNCH(bound_scan_coop_kernel, ceil_div(n, coop::GROUPS_PER_BLOCK), stream, make_view(g), indicator, w1,
+                      rays_o, dirs, near, far, R, n_grid, thresh, bnear, bfar);
+    }
+    NMB_LAUNCH_OK();
+    return 0;
+  }
   if (R >= RAY_KERNEL_MIN_RAYS) {
     const int64_t nseg = ceil_div(n_grid, BOUND_SEG);
     bound_rays_kernel<<<(unsigned)ceil_div(R * nseg, 128), 128, 0, stream>>>(

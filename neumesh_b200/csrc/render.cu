@@ -120,6 +120,51 @@ __global__ void coarse_z_kernel(int64_t R, int S, const float* __restrict__ near
   z[i] = __fadd_rn(__fmul_rn(near[r], __fsub_rn(1.0f, t)), __fmul_rn(far[r], t));
 }
 
+// torch.sum over a contiguous fp32 row of n elements as ATen's CPU kernel computes it (SumKernel.cpp, the path
+// `weights.sum(dim=-1)` of rend_util.py:281 takes; checked against torch 2.11 for every n <= 255, AVX2 and AVX512
+// builds alike): the row is read as 8-lane vectors; four vector accumulators take vectors 4i, 4i+1, 4i+2, 4i+3, leftover
+// vectors go to accumulator 0, the accumulators are folded 0 += 1, 2, 3; then a scalar starts from 0, adds the tail
+// elements (n % 8) in order and finally the 8 lanes in order.  Rows shorter than 8 use four scalar accumulators in the
+// same pattern.  sample_pdf's u = 1 sample (searchsorted against a cdf that saturates at 1.0 or not) depends on these
+// bits, so the normalisation constant is reproduced exactly rather than summed sequentially.
+__device__ __forceinline__ float torch_row_sum(const float* __restrict__ x, int64_t stride, int n) {
+  if (n < 8) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    const int q = n / 4;
+    if (q) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a[k] = __fadd_rn(a[k], x[k * stride]);
+    }
+    for (int i = q * 4; i < n; ++i) a[0] = __fadd_rn(x[i * stride], a[0]);
+    a[0] = __fadd_rn(a[0], a[1]);
+    a[0] = __fadd_rn(a[0], a[2]);
+    return __fadd_rn(a[0], a[3]);
+  }
+  float acc[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int l = 0; l < 8; ++l) acc[k][l] = 0.f;
+  const int nvec = n / 8, nblk = nvec / 4;
+  for (int b = 0; b < nblk; ++b) {
+#pragma unroll
+    for (int t = 0; t < 32; ++t) acc[t / 8][t % 8] = __fadd_rn(acc[t / 8][t % 8], x[(int64_t)(b * 32 + t) * stride]);
+  }
+  for (int v = nblk * 4; v < nvec; ++v) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) acc[0][l] = __fadd_rn(x[(int64_t)(v * 8 + l) * stride], acc[0][l]);
+  }
+#pragma unroll
+  for (int k = 1; k < 4; ++k)
+#pragma unroll
+    for (int l = 0; l < 8; ++l) acc[0][l] = __fadd_rn(acc[0][l], acc[k][l]);
+  float fin = 0.f;
+  for (int i = nvec * 8; i < n; ++i) fin = __fadd_rn(fin, x[(int64_t)i * stride]);
+#pragma unroll
+  for (int l = 0; l < 8; ++l) fin = __fadd_rn(fin, acc[0][l]);
+  return fin;
+}
+
 // One up-sampling iteration for one ray (renderer.py:209-245 + rend_util.py:276-319 with det=True).
 // n = current number of samples; writes n_new new depths (ascending) to znew[i][r].
 __global__ void __launch_bounds__(RT)
@@ -127,11 +172,12 @@ upsample_kernel(int64_t R, int n, int n_new, float inv_s, const float* __restric
                 float* __restrict__ wbuf, float* __restrict__ znew) {
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= R) return;
-  // pass 1: weights (sequential cumprod, as torch's CPU cumprod) and their sum
+  // pass 1: weights (sequential cumprod, as torch's CPU cumprod); their sum afterwards in torch's order
   float z0 = z[r], s0 = sdf[r];
   float prev_raw = 0.f;  // "prev_dot_val": raw slope of the previous interval, 0 for the first
-  float T = 1.0f;
-  float total = 0.f;
+  // torch's CPU cumprod / cumsum accumulate fp32 rows in DOUBLE (at::acc_type<float, false>) and round every output
+  // element to fp32: the running product / sum below are kept in double exactly like that
+  double T = 1.0;
   for (int j = 0; j + 1 < n; ++j) {
     const float z1 = z[(int64_t)(j + 1) * R + r], s1 = sdf[(int64_t)(j + 1) * R + r];
     const float mid = __fmul_rn(__fadd_rn(s0, s1), 0.5f);
@@ -144,25 +190,27 @@ upsample_kernel(int64_t R, int n, int n_new, float inv_s, const float* __restric
     const float c0 = sigmoid_t(__fmul_rn(__fsub_rn(mid, half), inv_s));
     const float c1 = sigmoid_t(__fmul_rn(__fadd_rn(mid, half), inv_s));
     const float alpha = __fdiv_rn(__fadd_rn(__fsub_rn(c0, c1), 1e-5f), __fadd_rn(c0, 1e-5f));
-    const float w = __fadd_rn(__fmul_rn(alpha, T), 1e-5f);  // alpha_to_w, then sample_pdf's "+ 1e-5"
-    T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f));
+    const float w = __fadd_rn(__fmul_rn(alpha, (float)T), 1e-5f);  // alpha_to_w, then sample_pdf's "+ 1e-5"
+    T = __dmul_rn(T, (double)__fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f));
     wbuf[(int64_t)j * R + r] = w;
-    total = __fadd_rn(total, w);
     z0 = z1;
     s0 = s1;
   }
+  const float total = torch_row_sum(wbuf + r, R, n - 1);
   // pass 2: inverse CDF at u_i = linspace(0,1,n_new); searchsorted(right=False): first j with cdf[j] >= u
   int i = 0;
   float u = linspace01(0, n_new);
   float cdf_prev = 0.f;           // cdf[j-1]
   float bin_prev = z[r];          // bins[j-1]
   float cdf_j = 0.f;              // cdf[0] = 0
+  double cdf_acc = 0.0;           // torch.cumsum's double accumulator
   float bin_j = bin_prev;
   for (int j = 0; j < n && i < n_new; ++j) {
     if (j > 0) {
       cdf_prev = cdf_j;
       bin_prev = bin_j;
-      cdf_j = __fadd_rn(cdf_j, __fdiv_rn(wbuf[(int64_t)(j - 1) * R + r], total));
+      cdf_acc = __dadd_rn(cdf_acc, (double)__fdiv_rn(wbuf[(int64_t)(j - 1) * R + r], total));
+      cdf_j = (float)cdf_acc;
       bin_j = z[(int64_t)j * R + r];
     }
     while (i < n_new && cdf_j >= u) {
@@ -238,13 +286,14 @@ composite_kernel(int64_t R, int P, float s, int white_bkgd, const float* __restr
   if (r >= R) return;
   const int64_t dst = perm[r];   // caller's ray index
   float c0 = sigmoid_t(__fmul_rn(sdf[r], s));
-  float T = 1.0f, acc = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
+  double T = 1.0;   // torch.cumprod on the CPU accumulates in double (see upsample_kernel)
+  float acc = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, nx = 0.f, ny = 0.f, nz = 0.f;
   for (int j = 0; j + 1 < P; ++j) {
     const int64_t q = (int64_t)j * R + r;
     const float c1 = sigmoid_t(__fmul_rn(sdf[q + R], s));
     const float alpha = fmaxf(__fdiv_rn(__fsub_rn(c0, c1), __fadd_rn(c0, 1e-10f)), 0.f);
-    const float w = __fmul_rn(alpha, T);
-    T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f));
+    const float w = __fmul_rn(alpha, (float)T);
+    T = __dmul_rn(T, (double)__fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f));
     wbuf[q] = w;
     acc = __fadd_rn(acc, w);
     cr = __fadd_rn(cr, __fmul_rn(w, rgb_s[q]));
@@ -298,14 +347,14 @@ weights_kernel(int64_t R, int P, float s, const float* __restrict__ sdf, float* 
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= R) return;
   float c0 = sigmoid_t(__fmul_rn(sdf[r], s));
-  float T = 1.0f;
+  double T = 1.0;   // as composite_kernel
   int n = 0;
   for (int j = 0; j + 1 < P; ++j) {
     const int64_t q = (int64_t)j * R + r;
     const float c1 = sigmoid_t(__fmul_rn(sdf[q + R], s));
     const float alpha = fmaxf(__fdiv_rn(__fsub_rn(c0, c1), __fadd_rn(c0, 1e-10f)), 0.f);
-    const float w = __fmul_rn(alpha, T);
-    T = __fmul_rn(T, __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f));
+    const float w = __fmul_rn(alpha, (float)T);
+    T = __dmul_rn(T, (double)__fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f));
     wbuf[q] = w;
     n += (w != 0.f) ? 1 : 0;
     c0 = c1;
@@ -554,6 +603,7 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
                int64_t rays_per_chunk, float* rgb, float* depth, float* acc, float* normals,
                const nmb_render_detail* detail, void* workspace, int64_t workspace_bytes, void* stream_) {
   using namespace nmb;
+  if (N <= 0) return 0;   // an empty shard: nothing to do (the output pointers of empty tensors are null)
   NMB_CHECK(f && cfg && rays_o && rays_d && rgb && depth && acc, "null argument");
   NMB_CHECK(rays_per_chunk > 0, "rays_per_chunk must be positive");
   NMB_CHECK(cfg->N_samples >= 2, "N_samples must be >= 2");
@@ -565,7 +615,6 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
   NMB_CHECK(rays_per_chunk * (int64_t)(cfg->N_samples + cfg->N_importance) < (int64_t(1) << 31),
             "rays_per_chunk x samples per ray must stay below 2^31 (32-bit live-sample offsets)");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (N <= 0) return 0;
   const int n_iters = cfg->N_upsample_iters;
   const int n_new = n_iters > 0 ? cfg->N_importance / n_iters : 0;
   const int P = cfg->N_samples + n_new * n_iters;

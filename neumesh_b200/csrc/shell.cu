@@ -205,7 +205,10 @@ int ensure_shell_grid(const nmb_field* f, cudaStream_t stream) {
   if (!(nmax == nmax) || nmax > 1e3) return 0;   // non-finite / absurd indicator vectors: no certificate
   // rho_safe: g(rho) = rho (rho^2 - w1 nmax) / (w1 + rho) >= threshold for every rho >= rho_safe
   const double w1 = f->w1, thr = (double)SHELL_THR + 1e-3;
+  // g is increasing once rho^2 > w1 nmax; if it is not yet above the threshold at the start of the search (very large
+  // learned indicator vectors, w1 * nmax > ~64) there is no sound rho_safe in range: build no certificate at all
   double rho_safe = 8.0;
+  if (rho_safe * (rho_safe * rho_safe - w1 * nmax) / (w1 + rho_safe) < thr) return 0;
   for (double rho = 8.0; rho > 0.0; rho -= 1e-3) {
     const double gval = rho * (rho * rho - w1 * nmax) / (w1 + rho);
     if (gval < thr) break;

@@ -63,20 +63,44 @@ def fused_eligible(model, rays_o, *, batched, perturb, random_color_direction, u
 def render_fused(rays_o, rays_d, model: NeuMesh, *, obj_bounding_radius=1.0, calc_normal=False, white_bkgd=False,
                  near_bypass=None, far_bypass=None, N_samples=64, N_importance=64, N_upsample_iters=4,
                  bounded_near_far=True, detailed_output=False, samples_output=False, chunk=None,
-                 normalize_dirs=True, skip_dead_samples=True):
+                 normalize_dirs=True, skip_dead_samples=True, min_chunk=None):
     """Flat [N,3] rays -> dict of flat outputs, through ``nmb_render``."""
     dev = rays_o.device
     o = rays_o.detach().reshape(-1, 3).float().contiguous()
     d = rays_d.detach().reshape(-1, 3).float().contiguous()
     N = o.shape[0]
+    if N == 0:
+        # an empty shard (multi-GPU renders of fewer than 128 * world rays leave some ranks without rays): same keys,
+        # empty tensors, no library call (empty tensors have null data pointers)
+        P = N_samples + (N_importance if N_upsample_iters > 0 else 0)
+        out = OrderedDict([("rgb", o.new_zeros(0, 3)), ("depth_volume", o.new_zeros(0)), ("mask_volume", o.new_zeros(0))])
+        if calc_normal:
+            out["normals_volume"] = o.new_zeros(0, 3)
+        if detailed_output:
+            if calc_normal:
+                out["implicit_nablas"] = o.new_zeros(0, P, 3)
+            out.update(implicit_surface=o.new_zeros(0, P), radiance=o.new_zeros(0, P - 1, 3), alpha=o.new_zeros(0, P - 1),
+                       cdf=o.new_zeros(0, P), visibility_weights=o.new_zeros(0, P - 1), d_final=o.new_zeros(0, P - 1),
+                       d_all=o.new_zeros(0, P), near_far=o.new_zeros(0, 2))
+            if samples_output:
+                out.update(xyz=o.new_zeros(0, P - 1, 3), dirs=o.new_zeros(0, P - 1, 3), density=o.new_zeros(0, P - 1, 1),
+                           colors=o.new_zeros(0, P - 1, 3))
+        return out
     cfg = _lib.RenderCfg(float(obj_bounding_radius), int(N_samples), int(N_importance), int(N_upsample_iters),
                          int(bool(bounded_near_far)), int(bool(calc_normal)), int(bool(white_bkgd)),
                          int(near_bypass is not None), float(near_bypass or 0.0), int(far_bypass is not None),
                          float(far_bypass or 0.0), int(bool(normalize_dirs)),
                          int(bool(skip_dead_samples) and not detailed_output))
-    chunk = int(min(chunk or DEFAULT_FUSED_CHUNK, max(N, 1)))
     field = model.packed_field()
     L = _lib.lib()
+    chunk = int(min(chunk or DEFAULT_FUSED_CHUNK, max(N, 1)))
+    if min_chunk is not None:
+        # the caller's ``rayschunk`` exists to bound memory (render.py passes 4096): never let the scratch of a chunk
+        # take more than half of the device memory that is free right now, but never go below the caller's own chunk
+        per_ray = L.nmb_render_workspace_bytes(C.byref(cfg), 1 << 16) / float(1 << 16)
+        cached = _WORKSPACES.get((dev.type, dev.index, torch.cuda.current_stream(dev).cuda_stream))
+        free = torch.cuda.mem_get_info(dev)[0] + (cached.numel() if cached is not None else 0)
+        chunk = int(min(chunk, max(int(min_chunk), int(0.5 * free / per_ray))))
     nbytes = L.nmb_render_workspace_bytes(C.byref(cfg), chunk)
     ws = _workspace(dev, nbytes)
     P = N_samples + (N_importance if N_upsample_iters > 0 else 0)
@@ -307,7 +331,7 @@ def volume_render(rays_o, rays_d, model, obj_bounding_radius=1.0, batched=False,
                            white_bkgd=white_bkgd, near_bypass=near_bypass, far_bypass=far_bypass,
                            N_samples=N_samples, N_importance=N_importance, N_upsample_iters=N_upsample_iters,
                            bounded_near_far=bounded_near_far, detailed_output=detailed_output,
-                           samples_output=samples_output)
+                           samples_output=samples_output, min_chunk=rayschunk)
         if batched:  # B == 1
             out = OrderedDict((k, v.unsqueeze(0)) for k, v in out.items())
         return out["rgb"], out["depth_volume"], out

@@ -5,7 +5,7 @@ Restates, function by function, ``models/mesh_grid.py:88-144`` (``compute_distan
 :204-237, ``_forward_color`` :239-260, ``compute_distance`` :262-273) and ``models/base.py:52-70`` (``Embedder``) as
 plain fp32 torch-CPU tensor code over a flat parameter dict (the reference's ``state_dict``).
 
-Pinned against the verbatim-imported reference by ``tests/test_oracle_vs_reference.py`` (run in the build
+Pinned against the verbatim-imported reference by ``tests/test_oracle.py::test_oracle_vs_unmodified_reference`` (run in the build
 container) and against ``tests/golden/*.npz`` everywhere else.  The KNN itself (third-party ``frnn``) is
 **parity unpinned** - see ``oracle/knn.py``.
 """

@@ -5,7 +5,7 @@ Restates ``models/renderer.py`` (``sdf_to_alpha`` :17-24, ``alpha_to_w`` :49-63,
 the un-batched, ``perturb=False`` case, as fp32 torch-CPU code over any object with the field protocol
 (``compute_distance``, ``forward_density_only``, ``forward_with_nablas``, ``forward``, ``forward_s``).
 
-Pinned against the verbatim-imported reference renderer by ``tests/test_oracle_vs_reference.py`` and the committed
+Pinned against the verbatim-imported reference renderer by ``tests/test_oracle.py::test_oracle_vs_unmodified_reference`` and the committed
 ``tests/golden/*.npz``.
 """
 from __future__ import annotations

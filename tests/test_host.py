@@ -112,3 +112,17 @@ def test_trained_like_fixture_is_sdf_like():
     ds, _, _ = f.compute_distance(x)
     sdf = f.forward_density_only(x)
     assert (sdf - ds).abs().max() < 0.05
+
+
+def test_render_fused_empty_shard_needs_no_library_call():
+    """A rank whose block-cyclic shard is empty (n_rays < 128 * world) must return empty outputs instead of handing
+    null pointers to ``nmb_render`` - the other ranks would otherwise hang in the image all-gather."""
+    from neumesh_b200 import parallel
+    from neumesh_b200.renderer import render_fused
+    assert parallel.shard_count(512, 5, 8) == 0 and parallel.shard_count(512, 3, 8) == 128
+    e = torch.empty(0, 3)
+    out = render_fused(e, e, model=None, calc_normal=True, detailed_output=True, samples_output=True)
+    assert out["rgb"].shape == (0, 3) and out["depth_volume"].shape == (0,) and out["normals_volume"].shape == (0, 3)
+    assert out["implicit_nablas"].shape == (0, 128, 3) and out["colors"].shape == (0, 127, 3)
+    full = parallel.gather_image({k: out[k] for k in ("rgb", "depth_volume", "mask_volume", "normals_volume")}, 0, 0, 1)
+    assert full["rgb"].shape == (0, 3)
