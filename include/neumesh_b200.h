@@ -128,7 +128,8 @@ int nmb_field_color(const nmb_field* f, const float* color_table, int64_t table_
 int nmb_field_shell_grid(const nmb_field* f, uint8_t* cells, int32_t* G, float* B, void* stream);
 
 /* ---- renderer ------------------------------------------------------------------------------------------------
- * volume_render (models/renderer.py:105-368), un-batched, perturb=False, no grad. */
+ * volume_render (models/renderer.py:105-368), un-batched, no grad (the sampling cascade of a training step included:
+ * perturb=True through caller-provided uniforms, sampling_only to stop after the cascade). */
 typedef struct nmb_render_cfg {
   float obj_bounding_radius;  /* 1.0 */
   int32_t N_samples;          /* 64 */
@@ -145,6 +146,13 @@ typedef struct nmb_render_cfg {
   int32_t skip_dead_samples;  /* 1: evaluate colour / mid-point nabla / normals only at samples whose visibility weight
                                  is not exactly 0 (the others are multiplied by 0.0f in renderer.py:304-333, so rgb, depth,
                                  acc and normals are bit-identical); ignored when per-sample detail outputs are requested */
+  int32_t sampling_only;      /* 1: stop after the sampling cascade (renderer.py:193-259) and export detail->d_all /
+                                 implicit_surface / near_far only: the no-grad half of a training step; rgb / depth / acc
+                                 are not written */
+  const float* perturb_u;     /* perturb=True (rend_util.py:292-295: u = torch.rand instead of linspace): device array
+                                 [N_upsample_iters][N_importance / N_upsample_iters][N] of uniforms in [0,1), each ray's
+                                 values ASCENDING within an iteration (the new samples are sorted into the old ones
+                                 anyway, so the order of the draws is immaterial); NULL = deterministic linspace */
 } nmb_render_cfg;
 
 /* optional per-sample outputs (renderer.py:335-348, detailed_output=True); any pointer may be NULL.
@@ -187,6 +195,71 @@ int nmb_pack_bgr8(const float* rgb, int64_t N, uint8_t* bgr8, void* stream);
  * normals must be rebuilt (editing/render_geometry_editing.py:37-67). */
 int nmb_vertex_normals(const float* vertices, int64_t V, const int32_t* triangles, int64_t T, float* normals,
                        void* stream);
+
+/* ---- training-path primitives (config 4: forward + backward through the field) -----------------------------------
+ * The reference trains through the renderer with autograd: models/trainer.py:75-80 (forward), :173-262 (losses on rgb,
+ * mask_volume, implicit_nablas, density, colors), neumesh.py:204-260 (field; the nabla comes from
+ * autograd.grad(create_graph=True), so the eikonal loss needs a double backward through the geometry MLP).  Here the
+ * field is one differentiable op (neumesh_b200/train_ops.py::FusedFieldFn) sequenced from these kernels; all tensors are
+ * dense row-major fp32 in the caller's layouts (torch parameter tensors, ORIGINAL vertex order, weights [out, in]).
+ * Derivation of the backward formulas and a float64 check against autograd: tools/train_math_proto.py. */
+
+/* C[M,N] (+)= A.B (+ bias[N]) with epilogue 0 none | 1 relu | 2 zero where mask[m*ldmask + n] <= 0.
+ * A(m,k) = a_kcontig ? A[m*lda + k] : A[k*lda + m];  B(k,n) = b_kcontig ? B[n*ldb + k] : B[k*ldb + n].
+ * (torch.nn.Linear forward: a_kcontig = b_kcontig = 1; dX = dZ.W: (1, 0); dW = dZ^T.X: (0, 0), split over K.) */
+int nmb_tr_gemm(const float* A, int64_t lda, int a_kcontig, const float* B, int64_t ldb, int b_kcontig, float* C,
+                int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, int epilogue, const float* mask,
+                int64_t ldmask, int accumulate, void* stream);
+
+typedef struct nmb_tr_inputs {
+  /* inputs */
+  const float* xyz;                /* [M,3] */
+  const float* dirs;               /* [M,3] view directions */
+  const int64_t* idx;              /* [M,8] neighbour indices (nmb_mesh_distance), original vertex order */
+  const float* w;                  /* [M,8] normalised inverse-distance weights (detached in the reference) */
+  const float* vertices;           /* [V,3] */
+  const float* indicator_vector;   /* [V,3] */
+  const float* geometry_features;  /* [V,geometry_dim] */
+  const float* color_features;     /* [V,color_dim] */
+  float indicator_weight;          /* sigmoid(indicator_weight_raw) or 0.1 */
+  int32_t geometry_dim, color_dim, multires_d, multires_fg, multires_ft, multires_view, enable_nablas_input;
+  int64_t M;
+  /* outputs of nmb_tr_prep (inputs of nmb_tr_input_bwd) */
+  float* ds;                       /* [M]   mesh distance (mesh_grid.py:121-144) */
+  float* G;                        /* [M,3] its closed-form gradient w.r.t. xyz */
+  float* Xg; int64_t ldg;          /* [M,ldg] geometry-MLP input: PE(ds) | PE(fg) | 0 (neumesh.py:214-217) */
+  float* T0; int64_t ldt;          /* [M,ldt] tangent seed d Xg / d ds = PE'(ds) | 0 */
+  float* Xc; int64_t ldc;          /* [M,ldc] colour-MLP input: nabla (by nmb_tr_geo_out_fwd) | PE(ds) | PE(view) | PE(ft) | 0 */
+} nmb_tr_inputs;
+
+/* gather + blend + encodings for M points (neumesh.py:11-13,214-217,248-258; base.py:52-70) */
+int nmb_tr_prep(const nmb_tr_inputs* in, void* stream);
+/* h = softplus_100(z), t = softplus'(z) * a over n elements (value and tangent rows of one hidden layer) */
+int nmb_tr_softplus_fwd(const float* z, const float* a, float* h, float* t, int64_t n, void* stream);
+/* ba = bt * softplus'(z);  bz = bh * softplus'(z) + bt * a * softplus''(z) */
+int nmb_tr_softplus_bwd(const float* z, const float* a, const float* bh, const float* bt, float* bz, float* ba,
+                        int64_t n, void* stream);
+/* sdf = h.w_out + b_out; g = t.w_out (= d sdf / d ds); nabla = g * G; nabla is also written to Xc[:, 0:3] if Xc */
+int nmb_tr_geo_out_fwd(const float* h, const float* t, const float* w_out, const float* b_out, const float* G,
+                       int64_t M, int32_t W, float* sdf, float* g, float* nabla, float* Xc, int64_t ldc, void* stream);
+/* rgb = sigmoid(c.w_out^T + b_out), w_out [3,W] */
+int nmb_tr_color_out_fwd(const float* c, const float* w_out, const float* b_out, int64_t M, int32_t W, float* rgb,
+                         void* stream);
+/* backward of color_out_fwd followed by the last ReLU: bz [M,W]; dw_out [3,W] and db_out [3] are ACCUMULATED */
+int nmb_tr_color_out_bwd(const float* b_rgb, const float* rgb, const float* c, const float* w_out, int64_t M, int32_t W,
+                         float* bz, float* dw_out, float* db_out, void* stream);
+/* out[n] += sum_m X[m*ldx + n] (bias gradients) */
+int nmb_tr_colsum(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* stream);
+/* backward of geo_out_fwd: upstream b_sdf [M] (nullable), b_nabla [M,3] (nullable) plus bXc[:, 0:3] (nullable: the
+ * colour MLP's input gradient); outputs bh, bt [M,W], b_G [M,3]; dw_out [W], db_out [1] ACCUMULATED */
+int nmb_tr_geo_out_bwd(const float* b_sdf, const float* b_nabla, const float* bXc, int64_t ldc, const float* G,
+                       const float* g, const float* h, const float* t, const float* w_out, int64_t M, int32_t W,
+                       float* bh, float* bt, float* b_G, float* dw_out, float* db_out, void* stream);
+/* backward of nmb_tr_prep: scatter-ADDS into d_geometry_features [V,Fg], d_color_features [V,Fc],
+ * d_indicator_vector [V,3], d_indicator_weight [1] (nullable) */
+int nmb_tr_input_bwd(const nmb_tr_inputs* in, const float* bXg, int64_t ldbg, const float* bT0, int64_t ldbt,
+                     const float* bXc, int64_t ldbc, const float* b_G, float* d_geometry_features,
+                     float* d_color_features, float* d_indicator_vector, float* d_indicator_weight, void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,7 +33,7 @@ class RenderCfg(C.Structure):
         ("N_upsample_iters", C.c_int32), ("bounded_near_far", C.c_int32), ("calc_normal", C.c_int32),
         ("white_bkgd", C.c_int32), ("use_near_bypass", C.c_int32), ("near_bypass", C.c_float),
         ("use_far_bypass", C.c_int32), ("far_bypass", C.c_float), ("normalize_dirs", C.c_int32),
-        ("skip_dead_samples", C.c_int32),
+        ("skip_dead_samples", C.c_int32), ("sampling_only", C.c_int32), ("perturb_u", C.c_void_p),
     ]
 
 
@@ -73,6 +73,18 @@ SIGNATURES = {
     "nmb_pack_bgr8": (C.c_int, [_P, _I64, _P, _P]),
     "nmb_vertex_normals": (C.c_int, [_P, _I64, _P, _I64, _P, _P]),
     "nmb_get_rays": (C.c_int, [C.POINTER(_F), C.POINTER(_F), _I32, _I32, _P, _P, _P]),
+    # training-path primitives (csrc/train.cu); the nmb_tr_inputs struct is bound in train_ops.TrInputs
+    "nmb_tr_gemm": (C.c_int, [_P, _I64, C.c_int, _P, _I64, C.c_int, _P, _I64, _I64, _I64, _I64, _P, C.c_int, _P, _I64,
+                              C.c_int, _P]),
+    "nmb_tr_prep": (C.c_int, [_P, _P]),
+    "nmb_tr_softplus_fwd": (C.c_int, [_P, _P, _P, _P, _I64, _P]),
+    "nmb_tr_softplus_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _P]),
+    "nmb_tr_geo_out_fwd": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _I64, _P]),
+    "nmb_tr_color_out_fwd": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P]),
+    "nmb_tr_color_out_bwd": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P]),
+    "nmb_tr_colsum": (C.c_int, [_P, _I64, _I64, _I64, _P, _P]),
+    "nmb_tr_geo_out_bwd": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P]),
+    "nmb_tr_input_bwd": (C.c_int, [_P, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P, _P, _P, _P]),
 }
 
 

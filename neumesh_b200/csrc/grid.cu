@@ -522,7 +522,7 @@ knn_distance_kernel(const float4* __restrict__ nodes, const float4* __restrict__
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB)
 knn_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts, const float4* __restrict__ indicator,
-                float w1, PointSrc src, int S, int seg, KnnOut out) {
+                float w1, PointSrc src, int S, int seg, KnnOut out, const GridView gv) {
   // thread t handles samples [g * seg, (g + 1) * seg) of ray r, t = g * R + r: with few rays (multi-GPU shards) a
   // ray's samples are split over several threads so that the launch still fills the GPU (one cold walk per segment)
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -544,7 +544,7 @@ knn_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts
       knn_walk<KNN_K, false>(nodes, pts, qx, qy, qz, d2, ix);
     } else {
       warm_rerank<KNN_K>(pts, qx, qy, qz, d2, ix);
-      knn_walk<KNN_K, true>(nodes, pts, qx, qy, qz, d2, ix);
+      knn_walk<KNN_K, true>(nodes, pts, qx, qy, qz, d2, ix, &gv);
     }
     float w[KNN_K], ds, grad[3];
     mesh_distance_point(pts, indicator, w1, qx, qy, qz, d2, ix, w, ds, grad);
@@ -568,7 +568,7 @@ knn_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts
 __global__ void __launch_bounds__(128)
 knn_lists_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts, const float4* __restrict__ indicator,
                  float w1, const float* __restrict__ xyz, const int32_t* __restrict__ off,
-                 const int32_t* __restrict__ cnt, int64_t R, int seg, int max_seg, KnnOut out) {
+                 const int32_t* __restrict__ cnt, int64_t R, int seg, int max_seg, KnnOut out, const GridView gv) {
   // thread t = g * R + r handles entries [g * seg, (g + 1) * seg) of ray r's list (short serial chains)
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t r = t % R;
@@ -586,7 +586,7 @@ knn_lists_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pt
       knn_walk<KNN_K, false>(nodes, pts, qx, qy, qz, d2, ix);
     } else {
       warm_rerank<KNN_K>(pts, qx, qy, qz, d2, ix);
-      knn_walk<KNN_K, true>(nodes, pts, qx, qy, qz, d2, ix);
+      knn_walk<KNN_K, true>(nodes, pts, qx, qy, qz, d2, ix, &gv);
     }
     float w[KNN_K], ds, grad[3];
     mesh_distance_point(pts, indicator, w1, qx, qy, qz, d2, ix, w, ds, grad);
@@ -609,7 +609,11 @@ knn_lists_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pt
 // group-cooperative kernels (knn_coop.cuh): 8 lanes per query chain, 16 chains per 128-thread block
 // ------------------------------------------------------------------------------------------------------------
 static bool knn_legacy() {
-  static const bool v = getenv("NMB_KNN_LEGACY") != nullptr;   // thread-per-query kernels (verification / A-B timing)
+  // Default: thread-per-query kernels (with the directory start).  NMB_KNN_COOP=1 selects the 8-lanes-per-query
+  // cooperative kernels instead: bit-identical results, measured 2.4x SLOWER on B200 (profiles/r2_ncu_knn_coop_summary.csv:
+  // 2.15x the warp instructions per query - shuffles, ranking, serial insertions - at 16 of 32 active lanes and 29
+  // resident warps), kept as the record of that experiment and as an independent implementation for cross-checks.
+  static const bool v = getenv("NMB_KNN_COOP") == nullptr;
   return v;
 }
 
@@ -809,7 +813,8 @@ int launch_knn_lists(const nmb_grid* g, const float4* indicator_sorted, float w1
   const int seg = 16;
   const int max_seg = (int)ceil_div(max_list, seg);
   knn_lists_kernel<<<(unsigned)ceil_div(R * max_seg, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1,
-                                                                            xyz, off, cnt, R, seg, max_seg, out);
+                                                                            xyz, off, cnt, R, seg, max_seg, out,
+                                                                            make_view(g));
   NMB_LAUNCH_OK();
   return 0;
 }
@@ -844,10 +849,11 @@ int launch_knn_distance(const nmb_grid* g, const float4* indicator_sorted, float
     const int seg = (int)ceil_div(S, nseg);
     nseg = ceil_div(S, seg);
     static const int minb = getenv("NMB_KNN_MINB") ? atoi(getenv("NMB_KNN_MINB")) : 10;
+    const GridView gv = make_view(g);
     const unsigned gridn = (unsigned)ceil_div(src.R * nseg, 128);
-    if (minb >= 12) knn_rays_kernel<12><<<gridn, 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src, S, seg, out);
-    else if (minb >= 10) knn_rays_kernel<10><<<gridn, 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src, S, seg, out);
-    else knn_rays_kernel<8><<<gridn, 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src, S, seg, out);
+    if (minb >= 12) knn_rays_kernel<12><<<gridn, 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src, S, seg, out, gv);
+    else if (minb >= 10) knn_rays_kernel<10><<<gridn, 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src, S, seg, out, gv);
+    else knn_rays_kernel<8><<<gridn, 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src, S, seg, out, gv);
     NMB_LAUNCH_OK();
     return 0;
   }
@@ -898,7 +904,7 @@ bound_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ p
                   const float4* __restrict__ indicator, float w1, const float* __restrict__ rays_o,
                   const float* __restrict__ dirs, const float* __restrict__ near, const float* __restrict__ far,
                   int64_t R, int n_grid, float thresh, int32_t* __restrict__ bnear, int32_t* __restrict__ bfar,
-                  ShellGrid shell) {
+                  ShellGrid shell, const GridView gv) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t r = t % R;
   const int s_begin = (int)(t / R) * BOUND_SEG;
@@ -935,7 +941,7 @@ bound_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ p
     have_prev = true;
     if (warm) {
       warm_rerank<KNN_K>(pts, qx, qy, qz, d2, ix);
-      knn_walk<KNN_K, true>(nodes, pts, qx, qy, qz, d2, ix);
+      knn_walk<KNN_K, true>(nodes, pts, qx, qy, qz, d2, ix, &gv);
     } else {
       knn_walk<KNN_K, false>(nodes, pts, qx, qy, qz, d2, ix);
     }
@@ -989,7 +995,7 @@ int launch_bound_scan(const nmb_grid* g, const float4* indicator, float w1, cons
     const int64_t nseg = ceil_div(n_grid, BOUND_SEG);
     bound_rays_kernel<<<(unsigned)ceil_div(R * nseg, 128), 128, 0, stream>>>(
         g->nodes.p, g->pts.p, indicator, w1, rays_o, dirs, near, far, R, n_grid, thresh, bnear, bfar,
-        (thresh == 0.1f) ? shell : ShellGrid{});
+        (thresh == 0.1f) ? shell : ShellGrid{}, make_view(g));
     NMB_LAUNCH_OK();
     return 0;
   }

@@ -60,14 +60,6 @@ __device__ __forceinline__ unsigned group_ballot(const Lane& ln, bool pred) {
   return (__ballot_sync(ln.gmask, pred) >> ln.gbase) & 0xFFu;
 }
 
-__device__ __forceinline__ uint32_t spread_bits10(uint32_t v) {
-  v = (v * 0x00010001u) & 0xFF0000FFu;
-  v = (v * 0x00000101u) & 0x0F00F00Fu;
-  v = (v * 0x00000011u) & 0xC30C30C3u;
-  v = (v * 0x00000005u) & 0x49249249u;
-  return v;
-}
-
 // Insert the group-uniform candidate (nd, ni) into the distributed ascending list (precondition: it ranks before the
 // entry of lane 7).  Lane k keeps its entry if the candidate ranks after it, takes the candidate if it ranks between the
 // entries of lanes k-1 and k, and takes lane k-1's entry otherwise.

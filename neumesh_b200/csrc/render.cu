@@ -169,7 +169,8 @@ __device__ __forceinline__ float torch_row_sum(const float* __restrict__ x, int6
 // n = current number of samples; writes n_new new depths (ascending) to znew[i][r].
 __global__ void __launch_bounds__(RT)
 upsample_kernel(int64_t R, int n, int n_new, float inv_s, const float* __restrict__ z, const float* __restrict__ sdf,
-                float* __restrict__ wbuf, float* __restrict__ znew) {
+                float* __restrict__ wbuf, float* __restrict__ znew, const float* __restrict__ u_arr /*[n_new][Nu] or null*/,
+                int64_t Nu, const int32_t* __restrict__ perm /*chunk ray -> caller ray (u_arr's column), or null*/) {
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= R) return;
   // pass 1: weights (sequential cumprod, as torch's CPU cumprod); their sum afterwards in torch's order
@@ -199,7 +200,9 @@ upsample_kernel(int64_t R, int n, int n_new, float inv_s, const float* __restric
   const float total = torch_row_sum(wbuf + r, R, n - 1);
   // pass 2: inverse CDF at u_i = linspace(0,1,n_new); searchsorted(right=False): first j with cdf[j] >= u
   int i = 0;
-  float u = linspace01(0, n_new);
+  const int64_t ucol = u_arr ? (perm ? (int64_t)perm[r] : r) : 0;
+  auto u_at = [&](int k) { return u_arr ? u_arr[(int64_t)k * Nu + ucol] : linspace01(k, n_new); };
+  float u = u_at(0);
   float cdf_prev = 0.f;           // cdf[j-1]
   float bin_prev = z[r];          // bins[j-1]
   float cdf_j = 0.f;              // cdf[0] = 0
@@ -222,7 +225,7 @@ upsample_kernel(int64_t R, int n, int n_new, float inv_s, const float* __restric
       const float t = __fdiv_rn(__fsub_rn(u, cb), denom);
       znew[(int64_t)i * R + r] = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(bin_j, bb)));
       ++i;
-      if (i < n_new) u = linspace01(i, n_new);
+      if (i < n_new) u = u_at(i);
     }
   }
   // u above the last cdf entry: inds = n -> below = above = n-1 -> denom = 0 -> 1 -> sample = bins[n-1]
@@ -604,12 +607,13 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
                const nmb_render_detail* detail, void* workspace, int64_t workspace_bytes, void* stream_) {
   using namespace nmb;
   if (N <= 0) return 0;   // an empty shard: nothing to do (the output pointers of empty tensors are null)
-  NMB_CHECK(f && cfg && rays_o && rays_d && rgb && depth && acc, "null argument");
+  NMB_CHECK(f && cfg && rays_o && rays_d, "null argument");
+  NMB_CHECK(cfg->sampling_only ? (detail != nullptr) : (rgb && depth && acc), "null output");
   NMB_CHECK(rays_per_chunk > 0, "rays_per_chunk must be positive");
   NMB_CHECK(cfg->N_samples >= 2, "N_samples must be >= 2");
   NMB_CHECK(cfg->N_upsample_iters >= 0 && (cfg->N_upsample_iters == 0 || cfg->N_importance % cfg->N_upsample_iters == 0),
             "N_importance must be a multiple of N_upsample_iters");
-  NMB_CHECK(!cfg->calc_normal || normals, "calc_normal needs a normals output");
+  NMB_CHECK(!cfg->calc_normal || normals || cfg->sampling_only, "calc_normal needs a normals output");
   NMB_CHECK(workspace_bytes >= nmb_render_workspace_bytes(cfg, rays_per_chunk), "workspace too small");
   NMB_CHECK(N < (int64_t(1) << 31), "at most 2^31 - 1 rays per call (32-bit ray permutation)");
   NMB_CHECK(rays_per_chunk * (int64_t)(cfg->N_samples + cfg->N_importance) < (int64_t(1) << 31),
@@ -706,18 +710,37 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
     const int64_t PR = (int64_t)P * R;
     const bool live_path = cfg->skip_dead_samples && !detail;
     // full path: nabla at every sample comes from the sampling passes; live path: only where the weight is non-zero
-    float* nab_pts = (cfg->calc_normal && !live_path) ? w.nabla_pts : nullptr;
-    float* nab_new = (cfg->calc_normal && !live_path) ? w.nabla_mid : nullptr;   // free until the mid-point pass
+    const bool carry_nabla = cfg->calc_normal && !live_path && !cfg->sampling_only;
+    float* nab_pts = carry_nabla ? w.nabla_pts : nullptr;
+    float* nab_new = carry_nabla ? w.nabla_mid : nullptr;   // free until the mid-point pass
     int rc = eval(w.z, n, w.sdf, nab_pts, false);
     if (rc) return rc;
     for (int it = 0; it < n_iters; ++it) {
-      upsample_kernel<<<rb, RT, 0, stream>>>(R, n, n_new, 256.0f * (float)(1 << it), w.z, w.sdf, w.wbuf, w.znew);
+      upsample_kernel<<<rb, RT, 0, stream>>>(R, n, n_new, 256.0f * (float)(1 << it), w.z, w.sdf, w.wbuf, w.znew,
+                                             cfg->perturb_u ? cfg->perturb_u + (int64_t)it * n_new * N : nullptr, N, perm);
       NMB_LAUNCH_OK();
       rc = eval(w.znew, n_new, w.sdfnew, nab_new, false);
       if (rc) return rc;
       merge_kernel<<<rb, RT, 0, stream>>>(R, n, n_new, w.z, w.sdf, w.znew, w.sdfnew, nab_pts, nab_new, PR);
       NMB_LAUNCH_OK();
       n += n_new;
+    }
+    if (cfg->sampling_only) {
+      // the no-grad half of a training step (renderer.py:199-259): sample depths (+ their sdf, near / far) only
+      if (detail && detail->d_all) {
+        export_samples_kernel<<<(unsigned)ceil_div(R * P, 256), 256, 0, stream>>>(R, P, 1, w.z, 0, perm, detail->d_all);
+        NMB_LAUNCH_OK();
+      }
+      if (detail && detail->implicit_surface) {
+        export_samples_kernel<<<(unsigned)ceil_div(R * P, 256), 256, 0, stream>>>(R, P, 1, w.sdf, 0, perm,
+                                                                                 detail->implicit_surface);
+        NMB_LAUNCH_OK();
+      }
+      if (detail && detail->near_far) {
+        export_near_far_kernel<<<rb, RT, 0, stream>>>(R, w.near, w.far, perm, detail->near_far);
+        NMB_LAUNCH_OK();
+      }
+      continue;
     }
     midpoints_kernel<<<(unsigned)ceil_div(R * (P - 1), 256), 256, 0, stream>>>(R, P, w.z, w.zmid);
     NMB_LAUNCH_OK();
@@ -812,7 +835,7 @@ int nmb_upsample_step(const float* z, const float* sdf, int64_t N, int32_t n, in
   NMB_CHECK(z && sdf && z_new && scratch && n >= 2 && n_new >= 1, "bad argument");
   if (N <= 0) return 0;
   nmb::upsample_kernel<<<(unsigned)nmb::ceil_div(N, nmb::RT), nmb::RT, 0, static_cast<cudaStream_t>(stream)>>>(
-      N, n, n_new, inv_s, z, sdf, scratch, z_new);
+      N, n, n_new, inv_s, z, sdf, scratch, z_new, nullptr, 0, nullptr);
   NMB_LAUNCH_OK();
   return 0;
 }

@@ -101,6 +101,9 @@ class NeuMesh(nn.Module):
         self.mlp_engine = mlp_engine
         self._field = None
         self._field_key = None
+        # grad-enabled queries on CUDA run the fused training op (train_ops.FusedFieldFn); False = torch-op path
+        self.fused_train = True
+        self._train_prims = None      # tests inject a torch implementation of the kernel interface here (CPU)
 
     # ------------------------------------------------------------------------------------------------------
     # packed CUDA field
@@ -235,9 +238,56 @@ class NeuMesh(nn.Module):
                 (rgb.reshape(*lead, 3) if rgb is not None else None), nbr)
 
     # ------------------------------------------------------------------------------------------------------
+    # fused training op (grad-enabled queries): CUDA forward + backward, see train_ops.py
+    # ------------------------------------------------------------------------------------------------------
+    def _fused_train_ok(self, *tensors) -> bool:
+        if not (self.fused_train and torch.is_grad_enabled()):
+            return False
+        c = self._cfg
+        if c["W"] != 256 or min(c["multires_d"], c["multires_fg"], c["multires_ft"], c["multires_view"]) < 0 \
+                or c["input_view_dim"] != 3 or c["input_d_dim"] != 1:
+            return False
+        if self._train_prims is not None:
+            return True
+        return all(t.is_cuda for t in tensors) and self.geometry_features.is_cuda \
+            and hasattr(self.mesh_grid, "grid") and hasattr(self.mesh_grid.grid, "handle")
+
+    def _train_field(self, xyz, view_dirs, with_color):
+        """-> (sdf [...,1], nabla [...,3], rgb [...,3] | None, (ds-less) neighbours (idx, w)), differentiable w.r.t. every
+        parameter; idx / w come from the CUDA octree (detached, as in mesh_grid.py:121-127)."""
+        from . import train_ops
+        lead = xyz.shape[:-1]
+        flat = xyz.detach().reshape(-1, 3).float().contiguous()
+        dirs = (view_dirs.detach().reshape(-1, 3).float().contiguous() if view_dirs is not None
+                else torch.zeros_like(flat))
+        w1_t = self.forward_indicator_weight().reshape(()) if self.learn_indicator_weight else \
+            torch.tensor(0.1, device=flat.device)
+        with torch.no_grad():
+            _, idx, w = self.mesh_grid.compute_distance(flat, indicator_vector=self.indicator_vector.detach(),
+                                                        indicator_weight=float(w1_t))
+        c = self._cfg
+        spec = train_ops.FieldSpec(c["geometry_dim"], c["color_dim"], c["multires_d"], c["multires_fg"], c["multires_ft"],
+                                   c["multires_view"], self.enable_nablas_input, c["D_density"], c["D_color"])
+        prims = self._train_prims if self._train_prims is not None else train_ops.CudaPrims(flat.device)
+        params = [self.indicator_vector, w1_t, self.geometry_features, self.color_features]
+        geo = self._geo_linears()
+        for lin in geo[:-1]:
+            params += [torch._weight_norm(lin.weight_v, lin.weight_g, 0), lin.bias]
+        params += [torch._weight_norm(geo[-1].weight_v, geo[-1].weight_g, 0), geo[-1].bias]
+        for lin in self._col_linears():
+            params += [lin.weight, lin.bias]
+        sdf, nabla, rgb = train_ops.FusedFieldFn.apply(spec, prims, bool(with_color), flat, dirs, idx, w,
+                                                       self.mesh_grid.get_vertices_torch(), *params)
+        return (sdf.reshape(*lead, 1), nabla.reshape(*lead, 3), rgb.reshape(*lead, 3) if with_color else None,
+                (idx.reshape(*lead, 8), w.reshape(*lead, 8)))
+
+    # ------------------------------------------------------------------------------------------------------
     # reference protocol (neumesh.py:113-174, 262-273)
     # ------------------------------------------------------------------------------------------------------
     def forward(self, xyz, view_dirs, need_nablas=True, nablas_only=False, return_ds=False):
+        if need_nablas and not return_ds and self._fused_train_ok(xyz, view_dirs):
+            sdf, nabla, rgb, _ = self._train_field(xyz, view_dirs, with_color=not nablas_only)
+            return (sdf, nabla) if nablas_only else (sdf, rgb)
         if self._fused_ok(xyz, view_dirs):
             if nablas_only:
                 sdf, nabla, _, nbr = self._fused_query(xyz, None, want_nabla=need_nablas,
@@ -262,12 +312,17 @@ class NeuMesh(nn.Module):
         return out
 
     def forward_density_only(self, xyz):
+        if self._fused_train_ok(xyz):
+            return self._train_field(xyz, None, with_color=False)[0]
         if self._fused_ok(xyz):
             return self._fused_query(xyz)[0]
         ds, indices, weights = self.compute_distance(xyz)
         return self._forward_density(xyz, ds, self.geometry_features, indices, weights, need_nablas=False)[0]
 
     def forward_with_nablas(self, xyz):
+        if self._fused_train_ok(xyz):
+            sdf, nabla, _, _ = self._train_field(xyz, None, with_color=False)
+            return sdf, nabla
         if self._fused_ok(xyz):
             sdf, nabla, _, _ = self._fused_query(xyz, None, want_nabla=True)
             return sdf, nabla

@@ -51,7 +51,7 @@ def fused_eligible(model, rays_o, *, batched, perturb, random_color_direction, u
         return False
     if not model.fused_supported() or not model.geometry_features.is_cuda:
         return False
-    if perturb or random_color_direction or not use_view_dirs:
+    if random_color_direction or not use_view_dirs:
         return False
     if batched and rays_o.shape[0] != 1:
         return False
@@ -63,8 +63,13 @@ def fused_eligible(model, rays_o, *, batched, perturb, random_color_direction, u
 def render_fused(rays_o, rays_d, model: NeuMesh, *, obj_bounding_radius=1.0, calc_normal=False, white_bkgd=False,
                  near_bypass=None, far_bypass=None, N_samples=64, N_importance=64, N_upsample_iters=4,
                  bounded_near_far=True, detailed_output=False, samples_output=False, chunk=None,
-                 normalize_dirs=True, skip_dead_samples=True, min_chunk=None):
-    """Flat [N,3] rays -> dict of flat outputs, through ``nmb_render``."""
+                 normalize_dirs=True, skip_dead_samples=True, min_chunk=None, perturb=False, perturb_u=None,
+                 sampling_only=False):
+    """Flat [N,3] rays -> dict of flat outputs, through ``nmb_render``.
+
+    ``perturb=True`` draws the up-sampling uniforms with ``torch.rand`` (``rend_util.py:292-295``); ``perturb_u``
+    [N_upsample_iters, N, N_importance / N_upsample_iters] injects them instead (parity runs).  ``sampling_only=True``
+    runs the no-grad sampling cascade only and returns ``{"d_all", "implicit_surface", "near_far"}``."""
     dev = rays_o.device
     o = rays_o.detach().reshape(-1, 3).float().contiguous()
     d = rays_d.detach().reshape(-1, 3).float().contiguous()
@@ -86,11 +91,19 @@ def render_fused(rays_o, rays_d, model: NeuMesh, *, obj_bounding_radius=1.0, cal
                 out.update(xyz=o.new_zeros(0, P - 1, 3), dirs=o.new_zeros(0, P - 1, 3), density=o.new_zeros(0, P - 1, 1),
                            colors=o.new_zeros(0, P - 1, 3))
         return out
+    u_dev = None
+    if (perturb or perturb_u is not None) and N_upsample_iters > 0:
+        n_new = N_importance // N_upsample_iters
+        u = perturb_u if perturb_u is not None else torch.rand(N_upsample_iters, N, n_new, device=dev)
+        u = u.to(dev).float().reshape(N_upsample_iters, N, n_new)
+        # the new samples are merged into the sorted ones, so only the SET of draws matters: each ray's ascending
+        u_dev = torch.sort(u, dim=-1)[0].permute(0, 2, 1).contiguous()      # [iters, n_new, N]
     cfg = _lib.RenderCfg(float(obj_bounding_radius), int(N_samples), int(N_importance), int(N_upsample_iters),
                          int(bool(bounded_near_far)), int(bool(calc_normal)), int(bool(white_bkgd)),
                          int(near_bypass is not None), float(near_bypass or 0.0), int(far_bypass is not None),
                          float(far_bypass or 0.0), int(bool(normalize_dirs)),
-                         int(bool(skip_dead_samples) and not detailed_output))
+                         int(bool(skip_dead_samples) and not detailed_output), int(bool(sampling_only)),
+                         u_dev.data_ptr() if u_dev is not None else None)
     field = model.packed_field()
     L = _lib.lib()
     chunk = int(min(chunk or DEFAULT_FUSED_CHUNK, max(N, 1)))
@@ -104,6 +117,15 @@ def render_fused(rays_o, rays_d, model: NeuMesh, *, obj_bounding_radius=1.0, cal
     nbytes = L.nmb_render_workspace_bytes(C.byref(cfg), chunk)
     ws = _workspace(dev, nbytes)
     P = N_samples + (N_importance if N_upsample_iters > 0 else 0)
+    if sampling_only:
+        out = OrderedDict([("d_all", torch.empty(N, P, device=dev)), ("implicit_surface", torch.empty(N, P, device=dev)),
+                           ("near_far", torch.empty(N, 2, device=dev))])
+        det = _lib.RenderDetail(out["d_all"].data_ptr(), out["implicit_surface"].data_ptr(), None, None, None,
+                                out["near_far"].data_ptr())
+        with torch.cuda.device(dev):
+            _lib.check(L.nmb_render(field, C.byref(cfg), _lib.ptr(o), _lib.ptr(d), N, chunk, None, None, None, None,
+                                    C.byref(det), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+        return out
     rgb = torch.empty(N, 3, device=dev)
     depth = torch.empty(N, device=dev)
     acc = torch.empty(N, device=dev)
@@ -177,13 +199,15 @@ def near_far_from_sphere(rays_o, rays_d, r=1.0, keepdim=True):
     return (mid - r).clamp_min(0.0), (mid + r).clamp_min(r)
 
 
-def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5):
+def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5, u=None):
     weights = weights + 1e-5
     pdf = weights / weights.sum(dim=-1, keepdim=True)
     cdf = torch.cumsum(pdf, dim=-1)
     cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
     shape = list(cdf.shape[:-1]) + [N_importance]
-    if det:
+    if u is not None:
+        u = u.expand(shape)     # caller-provided uniforms (parity runs of perturb=True)
+    elif det:
         u = torch.linspace(0.0, 1.0, steps=N_importance, device=cdf.device).expand(shape)
     else:
         u = torch.rand(shape, device=cdf.device)
@@ -232,11 +256,10 @@ def compute_bounded_near_far(model, rays_o, rays_d, near, far, sample_grid=256, 
     return torch.where(thin, lo - 0.05, lo), torch.where(thin, hi + 0.05, hi)
 
 
-def _render_generic(rays_o, rays_d, model, *, dim_batchify, obj_bounding_radius, calc_normal, use_view_dirs, netchunk,
-                    white_bkgd, near_bypass, far_bypass, detailed_output, perturb, N_samples, N_importance,
-                    N_upsample_iters, samples_output, bounded_near_far, random_color_direction):
+def _sample_cascade(rays_o, rays_d, model, query, *, obj_bounding_radius, near_bypass, far_bypass, perturb, N_samples,
+                    N_importance, N_upsample_iters, bounded_near_far, perturb_u=None):
+    """Torch-op sampling cascade (renderer.py:156-259) through the model protocol -> sorted depths z [..., P]."""
     dev = rays_o.device
-    query = lambda fn, *a: batchify_query(fn, *a, chunk=netchunk, dim_batchify=dim_batchify)  # noqa: E731
     near, far = near_far_from_sphere(rays_o, rays_d, r=obj_bounding_radius)
     if bounded_near_far:
         near, far = compute_bounded_near_far(model, rays_o, rays_d, near, far)
@@ -245,7 +268,6 @@ def _render_generic(rays_o, rays_d, model, *, dim_batchify, obj_bounding_radius,
     if far_bypass is not None:
         far = torch.full_like(far, far_bypass)
     pts_at = lambda z: rays_o.unsqueeze(-2) + z.unsqueeze(-1) * rays_d.unsqueeze(-2)  # noqa: E731
-
     t = torch.linspace(0, 1, N_samples, device=dev)
     with torch.no_grad():
         z = near * (1 - t) + far * t
@@ -261,11 +283,18 @@ def _render_generic(rays_o, rays_d, model, *, dim_batchify, obj_bounding_radius,
             c0 = cdf_Phi_s(mid - slope * dist * 0.5, inv_s)
             c1 = cdf_Phi_s(mid + slope * dist * 0.5, inv_s)
             alpha = (c0 - c1 + 1e-5) / (c0 + 1e-5)
-            z_new = sample_pdf(z, alpha_to_w(alpha), N_importance // N_upsample_iters, det=not perturb)
+            z_new = sample_pdf(z, alpha_to_w(alpha), N_importance // N_upsample_iters, det=not perturb,
+                               u=None if perturb_u is None else perturb_u[it])
             sdf_new = query(model.forward_density_only, pts_at(z_new)).squeeze(-1)
             z, order = torch.sort(torch.cat([z, z_new], dim=-1), dim=-1)
             sdf = torch.gather(torch.cat([sdf, sdf_new], dim=-1), -1, order)
-    z_all = z
+    return z
+
+
+def _render_from_samples(rays_o, rays_d, model, z_all, query, *, calc_normal, use_view_dirs, white_bkgd, detailed_output,
+                         samples_output, random_color_direction):
+    """Field evaluation at the final samples + compositing (renderer.py:264-348); differentiable."""
+    pts_at = lambda z: rays_o.unsqueeze(-2) + z.unsqueeze(-1) * rays_d.unsqueeze(-2)  # noqa: E731
     z_mid = 0.5 * (z_all[..., 1:] + z_all[..., :-1])
     pts, pts_mid = pts_at(z_all), pts_at(z_mid)
     if calc_normal:
@@ -309,13 +338,32 @@ def _render_generic(rays_o, rays_d, model, *, dim_batchify, obj_bounding_radius,
     return out
 
 
+def _render_generic(rays_o, rays_d, model, *, dim_batchify, obj_bounding_radius, calc_normal, use_view_dirs, netchunk,
+                    white_bkgd, near_bypass, far_bypass, detailed_output, perturb, N_samples, N_importance,
+                    N_upsample_iters, samples_output, bounded_near_far, random_color_direction, z_samples=None,
+                    perturb_u=None):
+    query = lambda fn, *a: batchify_query(fn, *a, chunk=netchunk, dim_batchify=dim_batchify)  # noqa: E731
+    if z_samples is None:
+        z_samples = _sample_cascade(rays_o, rays_d, model, query, obj_bounding_radius=obj_bounding_radius,
+                                    near_bypass=near_bypass, far_bypass=far_bypass, perturb=perturb, N_samples=N_samples,
+                                    N_importance=N_importance, N_upsample_iters=N_upsample_iters,
+                                    bounded_near_far=bounded_near_far, perturb_u=perturb_u)
+    return _render_from_samples(rays_o, rays_d, model, z_samples, query, calc_normal=calc_normal,
+                                use_view_dirs=use_view_dirs, white_bkgd=white_bkgd, detailed_output=detailed_output,
+                                samples_output=samples_output, random_color_direction=random_color_direction)
+
+
 def volume_render(rays_o, rays_d, model, obj_bounding_radius=1.0, batched=False, batched_info={}, calc_normal=False,
                   use_view_dirs=True, rayschunk=65536, netchunk=1048576, white_bkgd=False,
                   near_bypass: Optional[float] = None, far_bypass: Optional[float] = None, detailed_output=True,
                   show_progress=False, perturb=False, fixed_s_recp=1 / 64.0, N_samples=64, N_importance=64,
                   N_nograd_samples=2048, N_upsample_iters=4, samples_output=False, bounded_near_far=True,
-                  random_color_direction=False, **dummy_kwargs):
-    """rays_o, rays_d: [(B,) N_rays, 3] (directions need not be normalised) -> (rgb, depth_volume, extras)."""
+                  random_color_direction=False, perturb_u=None, z_samples=None, **dummy_kwargs):
+    """rays_o, rays_d: [(B,) N_rays, 3] (directions need not be normalised) -> (rgb, depth_volume, extras).
+
+    Beyond the reference's keywords (``renderer.py:105-135``): ``perturb_u`` [N_upsample_iters, N_rays, n] injects the
+    uniforms ``perturb=True`` would draw, ``z_samples`` [N_rays, P] skips the sampling cascade (teacher-forced depths);
+    both exist for parity runs of the training step."""
     if batched:
         dim_batchify, B = 1, rays_d.shape[0]
         flat_shape = [B, -1, 3]
@@ -331,12 +379,27 @@ def volume_render(rays_o, rays_d, model, obj_bounding_radius=1.0, batched=False,
                            white_bkgd=white_bkgd, near_bypass=near_bypass, far_bypass=far_bypass,
                            N_samples=N_samples, N_importance=N_importance, N_upsample_iters=N_upsample_iters,
                            bounded_near_far=bounded_near_far, detailed_output=detailed_output,
-                           samples_output=samples_output, min_chunk=rayschunk)
+                           samples_output=samples_output, min_chunk=rayschunk, perturb=perturb, perturb_u=perturb_u)
         if batched:  # B == 1
             out = OrderedDict((k, v.unsqueeze(0)) for k, v in out.items())
         return out["rgb"], out["depth_volume"], out
 
     rays_d = F.normalize(rays_d, dim=-1)
+    if (isinstance(model, NeuMesh) and torch.is_grad_enabled() and z_samples is None and rays_o.is_cuda
+            and model.fused_supported() and model.geometry_features.is_cuda and use_view_dirs
+            and (not batched or rays_o.shape[0] == 1) and N_samples >= 2
+            and (N_upsample_iters == 0 or N_importance % max(N_upsample_iters, 1) == 0)):
+        # training step (config 4): the no-grad sampling cascade runs in the fused CUDA kernels; the differentiable
+        # evaluation at the final samples goes through the model protocol below (FusedFieldFn on CUDA)
+        with torch.no_grad():
+            z_samples = render_fused(rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), model,
+                                     obj_bounding_radius=obj_bounding_radius, near_bypass=near_bypass,
+                                     far_bypass=far_bypass, N_samples=N_samples, N_importance=N_importance,
+                                     N_upsample_iters=N_upsample_iters, bounded_near_far=bounded_near_far,
+                                     normalize_dirs=False, min_chunk=rayschunk, perturb=perturb, perturb_u=perturb_u,
+                                     sampling_only=True)["d_all"]
+        if batched:
+            z_samples = z_samples.unsqueeze(0)
     n = rays_o.shape[dim_batchify]
     pieces = []
     it = range(0, n, rayschunk)
@@ -354,7 +417,9 @@ def volume_render(rays_o, rays_d, model, obj_bounding_radius=1.0, batched=False,
             near_bypass=near_bypass, far_bypass=far_bypass, detailed_output=detailed_output, perturb=perturb,
             N_samples=N_samples, N_importance=N_importance, N_upsample_iters=N_upsample_iters,
             samples_output=samples_output, bounded_near_far=bounded_near_far,
-            random_color_direction=random_color_direction))
+            random_color_direction=random_color_direction,
+            z_samples=None if z_samples is None else z_samples[sl],
+            perturb_u=None if perturb_u is None else (perturb_u[(slice(None),) + sl] if not batched else perturb_u)))
     ret = OrderedDict((k, torch.cat([p[k] for p in pieces], dim=dim_batchify)) for k in pieces[0])
     return ret["rgb"], ret["depth_volume"], ret
 

@@ -64,7 +64,7 @@ def mesh_bounded_near_far(field, o, d, near, far, n_grid=256, thresh=0.1):
 
 
 def _render_chunk(field, o, d, *, radius, calc_normal, white_bkgd, n_samples, n_importance, n_iters, bounded,
-                  near_bypass, far_bypass, detailed):
+                  near_bypass, far_bypass, detailed, perturb_u=None):
     near, far = sphere_near_far(o, d, radius)
     if bounded:
         near, far = mesh_bounded_near_far(field, o, d, near, far)
@@ -91,7 +91,9 @@ def _render_chunk(field, o, d, *, radius, calc_normal, white_bkgd, n_samples, n_
         inv_s = 256 * (2 ** it)
         c0, c1 = torch.sigmoid(est0 * inv_s), torch.sigmoid(est1 * inv_s)
         alpha = (c0 - c1 + 1e-5) / (c0 + 1e-5)
-        z_new = inverse_cdf_samples(z, transmittance_weights(alpha), n_importance // n_iters)
+        # perturb=True (rend_util.py:292-295) draws u = torch.rand; parity runs inject the draws: perturb_u [iters, N, n]
+        z_new = inverse_cdf_samples(z, transmittance_weights(alpha), n_importance // n_iters,
+                                    u=None if perturb_u is None else perturb_u[it])
         sdf_new = field.forward_density_only(pts_at(z_new)).squeeze(-1)
         z, order = torch.sort(torch.cat([z, z_new], dim=-1), dim=-1)
         sdf = torch.gather(torch.cat([sdf, sdf_new], dim=-1), -1, order)
@@ -127,8 +129,9 @@ def _render_chunk(field, o, d, *, radius, calc_normal, white_bkgd, n_samples, n_
 
 def volume_render(rays_o, rays_d, field, obj_bounding_radius=1.0, calc_normal=False, rayschunk=65536,
                   white_bkgd=False, near_bypass=None, far_bypass=None, detailed_output=False, N_samples=64,
-                  N_importance=64, N_upsample_iters=4, bounded_near_far=True, **_ignored):
-    """renderer.py:105-368, un-batched, perturb=False.  Returns (rgb [N,3], depth [N], extras)."""
+                  N_importance=64, N_upsample_iters=4, bounded_near_far=True, perturb_u=None, **_ignored):
+    """renderer.py:105-368, un-batched; perturb=False, or perturb=True with the uniforms given as ``perturb_u``
+    [N_upsample_iters, N, N_importance / N_upsample_iters].  Returns (rgb [N,3], depth [N], extras)."""
     o = rays_o.reshape(-1, 3).float()
     d = F.normalize(rays_d.reshape(-1, 3).float(), dim=-1)
     chunks = []
@@ -138,6 +141,7 @@ def volume_render(rays_o, rays_d, field, obj_bounding_radius=1.0, calc_normal=Fa
                                         calc_normal=calc_normal, white_bkgd=white_bkgd, n_samples=N_samples,
                                         n_importance=N_importance, n_iters=N_upsample_iters,
                                         bounded=bounded_near_far, near_bypass=near_bypass, far_bypass=far_bypass,
-                                        detailed=detailed_output))
+                                        detailed=detailed_output,
+                                        perturb_u=None if perturb_u is None else perturb_u[:, s:s + rayschunk]))
     out = {k: torch.cat([c[k] for c in chunks], dim=0) for k in chunks[0]}
     return out["rgb"], out["depth_volume"], out

@@ -86,12 +86,25 @@ def make_train_case(name, level, n_rays, seed):
     o, d = synth.frame_rays(24, 24, view=2)
     sel = torch.linspace(0, o.shape[0] - 1, n_rays).long()
     o, d = o[sel].contiguous(), d[sel].contiguous()
+    # record the final sample depths the reference's cascade produces (d_all is not among its outputs): the points
+    # handed to forward_with_nablas are rays_o + d_all * normalize(rays_d) (renderer.py:264)
+    seen = {}
+    fwn = model.forward_with_nablas
+
+    def spy(xyz):
+        seen["pts"] = xyz.detach().clone()
+        return fwn(xyz)
+
+    model.forward_with_nablas = spy
     rgb, depth, ex = ns.renderer.volume_render(o, d, model, rayschunk=4096, **helpers.TRAIN_KW)
+    model.forward_with_nablas = fwn
+    dn = torch.nn.functional.normalize(d, dim=-1)
+    d_all = ((seen["pts"].reshape(o.shape[0], -1, 3) - o[:, None, :]) * dn[:, None, :]).sum(-1)
     loss = helpers.train_loss(rgb, depth, ex)
     loss.backward()
     params = dict(model.named_parameters())
     out = dict(level=np.int64(level), seed=np.int64(seed), state_digest=np.array(state_digest(sd)),
-               rays_o=o.numpy(), rays_d=d.numpy(), loss=np.float64(loss.item()))
+               rays_o=o.numpy(), rays_d=d.numpy(), loss=np.float64(loss.item()), d_all=d_all.numpy())
     for k in helpers.GRAD_KEYS:
         g = params[k].grad
         out["grad_" + k] = g.numpy() if g.numel() < 20000 else g.numpy()[::7]
@@ -137,6 +150,9 @@ def make_texture_case(name, seed):
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "texture":
         make_texture_case("texture_edit_small", seed=40)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        make_train_case("train_step_small", 3, 48, seed=30)
         return
     cfg = synth.ModelConfig()
     make_case("scan63like_small", 4, 12, 12, cfg,

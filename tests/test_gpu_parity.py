@@ -11,8 +11,11 @@ asserted in two complementary ways:
   * teacher-forced: the oracle evaluates the field at the CUDA path's own final sample depths and composites -
     must match on EVERY ray within 1e-4 / 1e-5; each sampling stage is checked with identical inputs
     (test_upsample_step_*, test_bounded_near_far);
-  * free-running: whole-pipeline agreement, asserted as a fraction of rays not worse than the oracle's own
-    one-ulp noise floor.
+  * free-running: whole-pipeline agreement against renders of the UNMODIFIED reference on >= 4 000 rays of a real
+    800 x 800 frame per config (tests/golden/frame_config*.npz): the fraction of rays outside (1e-4, 1e-5) must not exceed
+    the fraction the reference ITSELF moves by when its sdf is perturbed at the fp32-evaluation level (sigma 4e-7,
+    stored in the same files) by more than three binomial standard deviations.  Small-frame comparisons use the same
+    rule with the frame-level floor (``outlier_bound``).
 """
 import os
 
@@ -29,6 +32,14 @@ ENGINES = ["fp32", "tcgen05"]
 if os.environ.get("NMB_TEST_F16") == "1":   # experimental fp16x3 engine: opt-in until validated
     ENGINES.append("tcgen05_f16")
 RGB_TOL, DEPTH_TOL = 1e-4, 1e-5
+# measured self-noise floors of the unmodified reference (tests/golden/make_frame_golden.py: fraction of rays of an
+# 800 x 800 frame that leave (1e-4, 1e-5) when the reference's own sdf is perturbed by sigma = 4e-7)
+REF_FLOOR = {"config1": 0.0565, "config3": 0.0634}
+
+
+def outlier_bound(floor, n):
+    """Largest outlier fraction compatible with the reference's own noise floor on n rays: floor + 3 binomial sigmas."""
+    return floor + 3.0 * (floor * (1.0 - floor) / n) ** 0.5
 
 
 def _dev():
@@ -346,15 +357,17 @@ def test_render_teacher_forced(case5, engine):
     # RGB: the north-star bar, every ray.
     assert e_rgb <= RGB_TOL
     # Depth: the reference's depth = sum(w / (sum(w) + 1e-10) * z) divides by the accumulated opacity, so it is
-    # ill-conditioned as acc -> 0 (grazing rays); the 1e-5 bar applies where depth is defined (acc >= 0.5).  Two fp32
-    # evaluations of the SAME sdf network (MKL sgemm vs these kernels) differ by ~1e-6 in sdf, which the sharpness
-    # s ~ 245 turns into up to ~1-2e-5 of depth on the worst ray: the bar is asserted at the 99th percentile, the
-    # worst ray at 3e-5, and - the meaningful statement - the CUDA path's distance to the float64 truth is of the
-    # same order as that of the reference's own fp32 arithmetic (measured: sdf max error 1.7e-6 for the 3xTF32
-    # tensor-core path and 2.3e-6 for the FFMA path vs 0.6e-6 for MKL sgemm; asserted within 4x + 4e-6).
-    assert dd[solid].quantile(0.99).item() <= DEPTH_TOL and dd[solid].max().item() <= 3e-5
+    # ill-conditioned as acc -> 0 (grazing rays).  Two fp32 evaluations of the SAME sdf network (MKL sgemm vs these
+    # kernels) differ by ~1e-6 in sdf, which the sharpness s ~ 245 amplifies.  Also asserted: the CUDA path's distance to
+    # the float64 truth is of the same order as that of the reference's own fp32 arithmetic.
+    # round-2 bounds = measured values (tcgen05 / fp32 engine: depth 7.4e-6 / 8.8e-6, depth * acc 5.0e-6 / 8.2e-6, acc
+    # 1.1e-4 / 1.3e-4, normals 1.1e-4) with at most 2x head-room: the depth bar holds on EVERY ray with acc >= 0.5, and
+    # on the low-opacity rays (where depth = sum(w z) / sum(w) is ill-conditioned as sum(w) -> 0) for depth * acc, the
+    # quantity that is composited into an image
+    assert dd[solid].max().item() <= DEPTH_TOL
+    assert (dd * acc.clamp_min(1e-6)).max().item() <= DEPTH_TOL
     assert c_dep <= 4 * o_dep + 4e-6 and c_rgb <= 2 * o_rgb + 2e-5
-    assert e_acc <= 3e-4 and e_nrm <= 5e-4
+    assert e_acc <= 2.7e-4 and e_nrm <= 2.5e-4
 
 
 @pytest.mark.parametrize("engine", ENGINES)
@@ -373,7 +386,9 @@ def test_render_free_running_vs_oracle_and_golden(golden_dir, engine):
         ok = ((dr <= RGB_TOL) & (dd <= DEPTH_TOL)).float().mean().item()
         print(f"[{engine}] {name}: rays within (1e-4, 1e-5) of the reference's golden render: {ok:.3f}; "
               f"median rgb {dr.median():.2e} depth {dd.median():.2e}; max rgb {dr.max():.2e} depth {dd.max():.2e}")
-        assert ok >= 0.85 and dr.median() <= 1e-5 and dd.median() <= 2e-6
+        # 144 / 100 rays: bound from the frame-level noise floor of the reference (see test_frame_parity_...)
+        assert 1.0 - ok <= outlier_bound(REF_FLOOR["config1"], dr.numel())
+        assert dr.median() <= 1e-6 and dd.median() <= 1e-6
         assert set(["rgb", "depth_volume", "mask_volume"]) <= set(ex.keys())
 
 
@@ -413,7 +428,7 @@ def test_render_noise_floor(case5):
     print(f"rays outside (1e-4,1e-5): oracle self-noise floor {floor:.4f}; CUDA fp32 {res['fp32']:.4f}; "
           f"CUDA tcgen05 {res['tcgen05']:.4f}")
     for engine in ENGINES:
-        assert res[engine] <= 2 * floor + 0.02
+        assert res[engine] <= outlier_bound(floor, o.shape[0]), (engine, res[engine], floor)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -574,7 +589,7 @@ def test_render_kwargs_fused_vs_generic_path(case5, kw):
     dd = (depth[0] - ref["depth_volume"]).abs()
     ok = ((dr <= RGB_TOL) & (dd <= DEPTH_TOL)).float().mean().item()
     print(f"{kw}: rays within (1e-4, 1e-5): {ok:.3f}; median rgb {dr.median():.1e} depth {dd.median():.1e}")
-    assert ok >= 0.90 and dr.median() <= 2e-6 and dd.median() <= 1e-6
+    assert ok >= 0.98 and dr.median() <= 2e-6 and dd.median() <= 1e-6   # measured 0.992 - 1.000 (same field bits)
     assert (ex["mask_volume"][0] - ref["mask_volume"]).abs().median() <= 1e-6
     if full.get("calc_normal"):
         assert (ex["normals_volume"][0] - ref["normals_volume"]).abs().max(-1)[0].median() <= 1e-5
@@ -649,14 +664,14 @@ def test_config3_wide_vertex_codes_vs_oracle(dims):
     ok = ((dr <= RGB_TOL) & (dd <= DEPTH_TOL)).float().mean().item()
     print(f"codes {dims}: rays within (1e-4, 1e-5) of the oracle render: {ok:.3f}; median rgb {dr.median():.1e} "
           f"depth {dd.median():.1e}")
-    assert ok >= 0.85 and dr.median() <= 1e-5 and dd.median() <= 2e-6
+    assert 1.0 - ok <= outlier_bound(REF_FLOOR["config3"], dr.numel()) and dr.median() <= 1e-6 and dd.median() <= 1e-6
 
 
 def test_config5_large_mesh_256_samples_per_ray():
     """BASELINE.json configs[4] at test size: a 2.6 M-vertex mesh (icosphere level 9), N_samples = N_importance = 128
     (256 samples per ray, 32 per up-sampling iteration).  Point-wise parity against the oracle on the big mesh, then
     size-independent properties on a 512 x 512 crop of the frame (certificate path), then free-running parity on a
-    handful of rays."""
+    4 000 rays of the frame (test_frame_parity_vs_reference_noise_floor[config5])."""
     import neumesh_b200 as nb
     from neumesh_b200.renderer import render_fused
     from oracle import render as orender
@@ -681,7 +696,7 @@ def test_config5_large_mesh_256_samples_per_ray():
     assert torch.equal(oknn._sq_dist_f32(x, pv, idx.cpu()), oknn._sq_dist_f32(x, pv, idx_ref))
     same = (idx.cpu() == idx_ref).all(dim=1)
     print(f"config 5: queries with identical neighbour lists {same.float().mean():.4f} (rest: exact fp32 distance ties)")
-    assert same.float().mean() > 0.9
+    assert same.float().mean() > 0.97      # measured 0.9858; the distances above are bit-identical on EVERY query
     assert (ds.cpu() - ds_ref)[same].abs().max() < 2e-6
     assert (sdf.cpu() - s_ref)[same].abs().max() < 5e-6 and (rgb.cpu() - c_ref)[same].abs().max() < 5e-6
     kw = dict(N_samples=128, N_importance=128, N_upsample_iters=4, calc_normal=True, white_bkgd=True,
@@ -699,27 +714,51 @@ def test_config5_large_mesh_256_samples_per_ray():
         assert torch.equal(a[k][:50000], b[k]), f"{k}: chunked render (plain bound scan) differs"
     acc = a["mask_volume"]
     assert acc.min() >= 0 and acc.max() <= 1 + 1e-4 and (acc > 0.99).float().mean() > 0.1
-    sel = torch.arange(0, o.shape[0], o.shape[0] // 96)[:96]
-    r_ref, d_ref, _ = orender.volume_render(o[sel].cpu(), d[sel].cpu(), f, **kw)
-    dr = (a["rgb"][sel].cpu() - r_ref).abs().max(-1)[0]
-    dd = (a["depth_volume"][sel].cpu() - d_ref).abs()
-    out = 1 - ((dr <= RGB_TOL) & (dd <= DEPTH_TOL)).float().mean().item()
+    # free-running parity of this config against the unmodified reference: test_frame_parity_vs_reference_noise_floor
 
-    # With 256 samples per ray the sampling cascade is far more rounding-sensitive than at 128: the yardstick is how
-    # much the ORACLE moves when its own sdf values are perturbed at the fp32-evaluation level (test_render_noise_floor)
-    class Noisy:
-        def __init__(self, base):
-            self.b, self.g = base, torch.Generator().manual_seed(9)
 
-        def __getattr__(self, k):
-            return getattr(self.b, k)
-
-        def forward_density_only(self, xx):
-            y = self.b.forward_density_only(xx)
-            return y + 4e-7 * torch.randn(y.shape, generator=self.g)
-
-    r_n, d_n, _ = orender.volume_render(o[sel].cpu(), d[sel].cpu(), Noisy(f), **kw)
-    floor = 1 - (((r_n - r_ref).abs().max(-1)[0] <= RGB_TOL) & ((d_n - d_ref).abs() <= DEPTH_TOL)).float().mean().item()
-    print(f"config 5 (V = {mesh.vertices.shape[0]}, 256 samples/ray): rays outside (1e-4, 1e-5) of the oracle: {out:.3f} "
-          f"(oracle self-noise floor {floor:.3f}); median rgb {dr.median():.1e} depth {dd.median():.1e}")
-    assert out <= floor + 0.15 and dr.median() <= 1e-5 and dd.median() <= 5e-6
+# ---------------------------------------------------------------------------------------------------------------
+# frame-scale free-running parity against the UNMODIFIED reference, with the reference's own noise floor as the bar
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["config1", "config3", "config5"])
+def test_frame_parity_vs_reference_noise_floor(golden_dir, name):
+    """>= 4 000 rays spread over a real 800 x 800 spiral frame per BASELINE config, rendered by the CUDA path and
+    compared with the render of the unmodified reference (tests/golden/make_frame_golden.py).  The reference's cascade is
+    discrete: perturbing ITS OWN sdf by sigma = 4e-7 (the level at which two fp32 evaluations of one network differ) moves
+    `floor` of the rays by more than (1e-4, 1e-5).  Bar: the CUDA path's outlier fraction <= floor + 3 binomial sigmas,
+    medians at rounding level."""
+    import neumesh_b200 as nb
+    path = os.path.join(golden_dir, f"frame_{name}.npz")
+    if not os.path.exists(path):
+        pytest.fail(f"{path} missing: run tests/golden/make_frame_golden.py {name} in the build container")
+    g = dict(np.load(path, allow_pickle=False))
+    dev = _dev()
+    cfg = synth.ModelConfig(**{k[4:]: int(v) for k, v in g.items() if k.startswith("cfg_")})
+    mesh = synth.icosphere_mesh(int(g["level"]), seed=0)
+    sd = synth.make_state_dict(mesh, cfg, seed=1)
+    assert helpers.state_digest(sd) == str(g["state_digest"])
+    kw = {k[3:]: (bool(v) if v.dtype == np.bool_ else int(v)) for k, v in g.items() if k.startswith("kw_")}
+    o, d = synth.frame_rays(800, 800, view=int(g["view"]))
+    sel = torch.from_numpy(g["sel"]).long()
+    o, d = o[sel].to(dev), d[sel].to(dev)
+    n = o.shape[0]
+    clean_rgb, clean_dep = torch.from_numpy(g["clean_rgb"]), torch.from_numpy(g["clean_depth"])
+    floor = 1.0 - (((torch.from_numpy(g["noisy_rgb"]) - clean_rgb).abs().max(-1)[0] <= RGB_TOL)
+                   & ((torch.from_numpy(g["noisy_depth"]) - clean_dep).abs() <= DEPTH_TOL)).float().mean().item()
+    for engine in (["tcgen05"] if name != "config1" else ENGINES):
+        model = helpers.cuda_model(mesh, cfg, sd, engine)
+        with torch.no_grad():
+            rgb, depth, ex = nb.volume_render(o, d, model, detailed_output=False, **kw)
+        dr = (rgb.cpu() - clean_rgb).abs().max(-1)[0]
+        dd = (depth.cpu() - clean_dep).abs()
+        da = (ex["mask_volume"].cpu() - torch.from_numpy(g["clean_acc"])).abs()
+        out = 1.0 - ((dr <= RGB_TOL) & (dd <= DEPTH_TOL)).float().mean().item()
+        mse = ((rgb.cpu() - clean_rgb) ** 2).mean().item()
+        psnr = float("inf") if mse == 0 else -10.0 * np.log10(mse)
+        bound = outlier_bound(floor, n)
+        print(f"[{name} / {engine}] {n} rays: outside (1e-4, 1e-5) of the reference: {out:.4f}; reference self-noise floor "
+              f"{floor:.4f} (bound {bound:.4f}); rgb median {dr.median():.1e} p99 {dr.quantile(0.99):.1e} max {dr.max():.1e}; "
+              f"depth median {dd.median():.1e} p99 {dd.quantile(0.99):.1e}; acc max {da.max():.1e}; PSNR vs reference {psnr:.1f} dB")
+        assert out <= bound, (name, engine, out, floor, bound)
+        assert dr.median() <= 1e-6 and dd.median() <= 2e-6 and psnr >= 70.0
+        del model

@@ -120,4 +120,5 @@ def test_texture_dropin_fused_vs_oracle_and_golden(golden_dir, engine):
     dd = (d.cpu() - torch.from_numpy(g["render_depth"])).abs()
     ok = ((dr <= 1e-4) & (dd <= 1e-5)).float().mean().item()
     print(f"[{engine}] texture edit render: rays within (1e-4, 1e-5) of the reference's golden: {ok:.3f}")
-    assert ok >= 0.85 and dr.median() <= 1e-5
+    # 100 rays: floor of the unmodified reference on a full frame (0.0565, tests/golden/frame_config1.npz) + 3 binomial sigmas
+    assert 1.0 - ok <= 0.0565 + 3.0 * (0.0565 * 0.9435 / dr.numel()) ** 0.5 and dr.median() <= 1e-6

@@ -59,11 +59,16 @@ def test_train_step_gradients_gpu(golden_dir):
     dev = torch.device("cuda:0")
     g, cfg, mesh, sd = _load(golden_dir)
     model = helpers.cuda_model(mesh, cfg, sd, "tcgen05").train()
+    model.fused_train = False   # this file covers the torch-op path; tests/test_train_ops.py covers the fused CUDA op
     o, d = torch.from_numpy(g["rays_o"]).to(dev), torch.from_numpy(g["rays_d"]).to(dev)
-    loss, params = _grads(model, o, d)
-    # same algorithm in fp32 on the GPU (cuBLAS / elementwise kernels round differently from MKL): the discrete
-    # sampling cascade makes a few samples move, so the match is looser than on CPU
-    _check(g, loss, params, rtol=2e-2, l2tol=0.2)
+    # sample depths teacher-forced to the reference's (the discrete cascade is compared separately): with identical
+    # samples the gradients agree to fp32 rounding (cuBLAS / elementwise kernels vs MKL)
+    rgb, depth, ex = nb.volume_render(o, d, model, rayschunk=4096, z_samples=torch.from_numpy(g["d_all"]).to(dev),
+                                      **helpers.TRAIN_KW)
+    loss_t = helpers.train_loss(rgb, depth, ex)
+    loss_t.backward()
+    loss, params = loss_t.item(), dict(model.named_parameters())
+    _check(g, loss, params, rtol=1e-3, l2tol=1e-3)
     # an optimiser step changes the parameters in place: the fused no-grad path must pick the new values up
     x = torch.rand(64, 3, device=dev) - 0.5
     with torch.no_grad():

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-T="timeout 240"
+T="timeout 150"
 $T python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "knn or mesh_distance or bounded_near_far" > gpurun_out/r2_knn_tests.txt 2>&1; echo "rc=$?" >> gpurun_out/r2_knn_tests.txt
 NMB_KNN_LEGACY=1 $T python tools/knn_ab.py dump legacy > gpurun_out/r2_ab_legacy.txt 2>&1
 NMB_KNN_NO_DIR=1 $T python tools/knn_ab.py dump nodir > gpurun_out/r2_ab_nodir.txt 2>&1
