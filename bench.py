@@ -30,6 +30,37 @@ H = W = 800
 MESH_LEVEL = 7
 RENDER_KW = dict(calc_normal=True, white_bkgd=True, bounded_near_far=True)
 METRIC = "rays_per_sec_800x800_spiral"
+DEFAULT_ENGINE = "tcgen05_f16"
+CODE_DIM = 32
+WORKLOAD_NAME = "spiral_800x800_icosphere_V163842_F32_K8"
+
+# BASELINE.json configs as bench workloads.  The default (and the only one the driver times) is the configuration the
+# headline metric is quoted on; the others are for `python bench.py --workload ...` measurements recorded in profiles/.
+WORKLOADS = {
+    "spiral800": dict(H=800, W=800, level=7, code=32, kw=RENDER_KW, name="spiral_800x800_icosphere_V163842_F32_K8"),
+    # config 2: "DTU scan63 full-res spiral" = 1600 x 1200 frames of the same scene
+    "scan63_full": dict(H=1200, W=1600, level=7, code=32, kw=RENDER_KW, name="spiral_1600x1200_icosphere_V163842_F32_K8"),
+    # config 3: "8-NN 256-d vertex codes", 800 x 800
+    "codes256": dict(H=800, W=800, level=7, code=256, kw=RENDER_KW, name="spiral_800x800_icosphere_V163842_F256_K8"),
+    # config 5: 2.6 M vertices, 256 samples per ray (image size from --image, default 4096 x 4096 split in bands)
+    "big": dict(H=4096, W=4096, level=9, code=32,
+                kw=dict(RENDER_KW, N_samples=128, N_importance=128, N_upsample_iters=4),
+                name="spiral_4096x4096_icosphere_V2621442_F32_K8_256spp"),
+}
+
+
+def set_workload(name, image=0):
+    global H, W, MESH_LEVEL, RENDER_KW, CODE_DIM, WORKLOAD_NAME, FLOP_GEO, FLOP_JVP, FLOP_COL
+    w = WORKLOADS[name]
+    H, W, MESH_LEVEL, RENDER_KW, CODE_DIM, WORKLOAD_NAME = w["H"], w["W"], w["level"], dict(w["kw"]), w["code"], w["name"]
+    if image:
+        H = W = int(image)
+        WORKLOAD_NAME = WORKLOAD_NAME.replace("4096x4096", f"{H}x{W}").replace("800x800", f"{H}x{W}")
+    kg, kc = 17 + 5 * CODE_DIM, 3 + 17 + 27 + 5 * CODE_DIM
+    FLOP_GEO = 2 * (kg * 256 + 2 * 256 * 256 + 256)
+    FLOP_JVP = 2 * (17 * 256 + 2 * 256 * 256 + 256)
+    FLOP_COL = 2 * (kc * 256 + 3 * 256 * 256 + 3 * 256)
+
 
 # algorithmic work per point (reference dims, no padding, each MAC counted once)
 FLOP_GEO = 2 * (177 * 256 + 2 * 256 * 256 + 256)          # 353 280
@@ -103,7 +134,7 @@ class ClockSampler:
 
 
 def build_inputs(n_frames: int):
-    cfg = synth.ModelConfig()
+    cfg = synth.ModelConfig(geometry_dim=CODE_DIM, color_dim=CODE_DIM)
     mesh = synth.icosphere_mesh(MESH_LEVEL, seed=0)
     sd = synth.make_state_dict(mesh, cfg, seed=1)
     frames = [synth.frame_rays(H, W, view=v, n_views=90) for v in range(n_frames)]
@@ -112,6 +143,7 @@ def build_inputs(n_frames: int):
 
 def cpu_oracle_rate(cfg, mesh, sd, o, d, n_rays: int, repeats: int = 1):
     """rays/s of the oracle port (reference algorithm, torch CPU fp32, cKDTree exact KNN) on a strided ray sample."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     from oracle import render as orender
     from oracle.field import FieldOracle
     f = FieldOracle(mesh.vertices, sd, cfg)
@@ -132,6 +164,8 @@ def run_reference(args, rank, world):
     travel to the GPU box), all host threads, bounded sample per step."""
     if rank != 0:
         return
+    # all the host threads the box has (torchrun exports OMP_NUM_THREADS=1 to every rank: override it)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     cfg, mesh, sd, frames = build_inputs(1)
     o, d = frames[0]
     n = args.ref_rays
@@ -162,9 +196,10 @@ def run_reference(args, rank, world):
 
 
 def workload_config(rays_per_step):
-    return {"workload": "spiral_800x800_icosphere_V163842_F32_K8", "image": [H, W], "rays_per_step": rays_per_step,
-            "mesh_vertices": 10 * 4 ** MESH_LEVEL + 2, "vertex_code_dim": 32, "knn_k": 8, "N_samples": 64,
-            "N_importance": 64, "render": RENDER_KW,
+    return {"workload": WORKLOAD_NAME, "image": [H, W], "rays_per_step": rays_per_step,
+            "mesh_vertices": 10 * 4 ** MESH_LEVEL + 2, "vertex_code_dim": CODE_DIM, "knn_k": 8,
+            "N_samples": RENDER_KW.get("N_samples", 64), "N_importance": RENDER_KW.get("N_importance", 64),
+            "render": RENDER_KW,
             "l2": "inputs larger than L2: every step renders a different spiral view and streams ~12 GB of per-sample "
                   "scratch per frame (126 MB L2)"}
 
@@ -175,8 +210,15 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "fp32", "tcgen05_f16"],
-                    help="MLP engine; tcgen05_f16 (fp16x3 operands) is experimental and not validated on hardware yet")
+    ap.add_argument("--engine", default=DEFAULT_ENGINE, choices=["tcgen05", "fp32", "tcgen05_f16"],
+                    help="MLP engine: tcgen05_f16 = fp16x3 operands (default), tcgen05 = 3xTF32, fp32 = CUDA cores")
+    ap.add_argument("--workload", default="spiral800", choices=sorted(WORKLOADS) + ["train"],
+                    help="spiral800 = the headline configuration (default, the one the driver times); scan63_full / "
+                         "codes256 / big = BASELINE configs 2 / 3 / 5; train = config 4 (512 rays per GPU per step)")
+    ap.add_argument("--image", type=int, default=0, help="override the (square) image size of the workload")
+    ap.add_argument("--shard", default="auto", choices=["auto", "frame", "rays"],
+                    help="multi-GPU partition of a step: whole frames per rank (when frames-per-step is a multiple of the "
+                         "world size) or block-cyclic blocks of 128 rays of the pooled frames")
     ap.add_argument("--chunk", type=int, default=0, help="rays per kernel chunk (0 = library default)")
     ap.add_argument("--ref-rays", type=int, default=1024, help="rays per step of the CPU reference arm")
     ap.add_argument("--cpu-rays", type=int, default=1536, help="rays of the cpu_baseline sample (0 = skip)")
@@ -195,6 +237,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload == "train":
+        import bench_train
+        bench_train.main(args, rank, world, local_rank)
+        return
+    set_workload(args.workload, args.image)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -223,8 +270,18 @@ def main():
     model.load_state_dict(sd)
     model = model.to(dev).eval()
     n_rays = H * W * fps                             # rays per step: `fps` consecutive spiral frames, pooled
-    sl = parallel.shard_indices(n_rays, rank, world * sim)   # block-cyclic: every rank gets the same hit / miss mix
-    n_mine = parallel.shard_count(n_rays, rank, world * sim)
+    # partition of a step over the ranks: whole frames when there is at least one per rank (a rank's Morton-ordered
+    # rays then belong to ONE camera pose - pooling blocks of eight different poses made the per-rank octree walks 30 %
+    # slower at 8 GPUs in round 1), block-cyclic blocks of 128 rays otherwise (single-frame latency mode)
+    by_frame = (args.shard == "frame" or (args.shard == "auto" and fps % world == 0 and fps >= world)) and sim == 1 \
+        and world > 1 and fps % world == 0
+    if by_frame:
+        per = (fps // world) * H * W
+        sl = torch.arange(rank * per, (rank + 1) * per)
+        n_mine = per
+    else:
+        sl = parallel.shard_indices(n_rays, rank, world * sim)   # block-cyclic: every rank gets the same hit / miss mix
+        n_mine = parallel.shard_count(n_rays, rank, world * sim)
     host = [(o[sl].contiguous().pin_memory(), d[sl].contiguous().pin_memory()) for o, d in frames]
     resident = [(o.to(dev), d.to(dev)) for o, d in host]
     chunk = args.chunk or None
@@ -235,6 +292,8 @@ def main():
                             **RENDER_KW)
         if sim > 1:
             return part
+        if by_frame:
+            return parallel.gather_image_contiguous(part, world)
         return parallel.gather_image(part, n_rays, rank, world)
 
     if sim > 1 or args.tune:
@@ -315,6 +374,10 @@ def main():
             d = d_h.to(dev, non_blocking=True)
             if world == 1 and not args.all_samples:
                 rgb, depth, _ = nb.volume_render(o, d, model, detailed_output=False, **RENDER_KW)
+            elif by_frame:
+                part = render_fused(o, d, model, chunk=chunk, skip_dead_samples=not args.all_samples, **RENDER_KW)
+                full = parallel.gather_image_contiguous(part, world)
+                rgb, depth = full["rgb"], full["depth_volume"]
             else:
                 full = parallel.render_sharded_local(o, d, model, n_rays, rank, world, chunk=chunk,
                                                      skip_dead_samples=not args.all_samples, **RENDER_KW)
@@ -371,15 +434,17 @@ def main():
         def tensor_roofline(k):
             peak = peaks["bf16_tflops_sustained"]
             ach = kern[k]["tflops_algorithmic"]
+            split = ("every MAC is issued 3x as kind::f16 (fp16x3 split operands, fp32-accurate; needed for the 1e-4 / 1e-5 "
+                     "parity bar), so the ceiling of this fraction is 1/3" if args.engine == "tcgen05_f16" else
+                     "every MAC is issued 3x as kind::tf32 (3xTF32 split) and TF32 runs at half the bf16 rate, so the "
+                     "ceiling of this fraction is 1/6")
             return {"bound": "tensor", "kernel": kname[k], "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                     "frac": ach / peak, "traffic": traffic_of(k),
                     "peak_source": f"{peaks['source']} dense bf16 cuBLAS, sustained",
                     "avg_launch_ms": kern[k]["ms_per_step"] / kern[k]["launches_per_step"],
                     "ms_per_step": kern[k]["ms_per_step"],
                     "note": "achieved = algorithmic fp32-equivalent FLOPs (each MAC once, reference dims) / device time "
-                            "of the kernel class; the kernel issues every MAC 3x as kind::tf32 (3xTF32 split, needed "
-                            "for the 1e-4/1e-5 parity bar) and TF32 runs at half the bf16 rate, so the ceiling of this "
-                            "fraction is 1/6 = 0.167 x (MMA shape efficiency); tensor-pipe active is ~60 % (ncu)"}
+                            "of the kernel class; " + split}
 
         def hbm_roofline(k):
             ach = kern[k]["gbs_algorithmic"]
@@ -410,20 +475,51 @@ def main():
                 if not parts:
                     return None
                 return sum(tab[kk] * kern[kk]["points_per_step"] for kk in parts) / kern[k]["launches_per_step"]
+            if k == "walk":
+                parts = [kk for kk in ("knn", "knn_list", "bound_scan") if kk in kern]
+                vals = [traffic_of(kk) for kk in parts]
+                if any(v is None for v in vals):
+                    return None
+                return sum(v * kern[kk]["launches_per_step"] for v, kk in zip(vals, parts)) / kern[k]["launches_per_step"]
             bpp = tab.get("knn" if k == "knn_list" else k)
             if bpp is None or k not in kern or not kern[k]["launches_per_step"]:
                 return None
             return bpp * kern[k]["points_per_step"] / kern[k]["launches_per_step"]
 
+        if walk:   # the three octree-walk kernels share knn_walk.cuh: one class, like the MLP instantiations
+            tot_ms = sum(kern[k]["ms_per_step"] for k in walk)
+            tot_pts = sum(kern[k]["points_per_step"] for k in walk)
+            kern["walk"] = {"ms_per_step": tot_ms, "launches_per_step": sum(kern[k]["launches_per_step"] for k in walk),
+                            "points_per_step": tot_pts, "gbs_algorithmic": tot_pts * BYTES_KNN / (tot_ms * 1e-3) / 1e9}
+            kname["walk"] = "knn_rays_kernel + knn_lists_kernel + bound_rays_kernel (exact 8-NN octree walks, all)"
+            walk = walk + ["walk"]
         roofline = None
+        secondary = None
         allk = mlp + walk
         if allk:
-            cand = [k for k in allk if k not in ("geo", "geo_jvp", "color")]   # MLP instantiations count once, together
-            dom = max(cand, key=lambda k: kern[k]["ms_per_step"])
-            roofline = tensor_roofline(dom) if dom in mlp else hbm_roofline(dom)
-            roofline["by_class"] = {k: (tensor_roofline(k) if k in mlp else hbm_roofline(k)) for k in allk}
+            # the two kernel CLASSES of the frame: every tcgen05 MLP instantiation together, every octree walk together
+            cls = [k for k in ("mlp_tc", "walk") if k in kern]
+            cls.sort(key=lambda k: -kern[k]["ms_per_step"])
+            mk = lambda k: tensor_roofline(k) if k in mlp else hbm_roofline(k)   # noqa: E731
+            roofline = mk(cls[0])
+            secondary = mk(cls[1]) if len(cls) > 1 else None
+            roofline["by_class"] = {k: mk(k) for k in allk}
             for v in roofline["by_class"].values():
                 v.pop("note", None)
+            walk_issue = traffic_tab.get("walk_issue")
+            if walk_issue and "walk" in kern:
+                # honest second roofline of the latency / issue-bound walks: warp instructions per query from the ncu
+                # capture of this very kernel x queries per second, against the SMs' issue rate at the sampled clock
+                sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+                qps = kern["walk"]["points_per_step"] / (kern["walk"]["ms_per_step"] * 1e-3)
+                peak = 148 * 4 * sm_mhz * 1e6
+                tgt = roofline if cls[0] == "walk" else secondary
+                tgt["issue_slots"] = {"warp_inst_per_query": walk_issue["warp_inst_per_query"],
+                                      "active_lanes_per_inst": walk_issue["active_lanes_per_inst"],
+                                      "achieved_warp_inst_per_s": qps * walk_issue["warp_inst_per_query"],
+                                      "peak_warp_inst_per_s": peak,
+                                      "frac": qps * walk_issue["warp_inst_per_query"] / peak,
+                                      "source": walk_issue.get("source", "profiles/")}
         cpu = None
         if world == 1 and args.cpu_rays > 0:
             rate, secs = cpu_oracle_rate(cfg, mesh, sd, frames[0][0], frames[0][1], args.cpu_rays)
@@ -437,15 +533,18 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None,
             "dtype": {"tcgen05": "fp32 (MLPs: 3xTF32 tcgen05, fp32 accumulate)",
-                      "tcgen05_f16": "fp32 (MLPs: fp16x3 tcgen05, fp32 accumulate; EXPERIMENTAL engine)"}.get(args.engine, "fp32"),
+                      "tcgen05_f16": "fp32 (MLPs: fp16x3 split operands on tcgen05 kind::f16, fp32 accumulate; sdf error "
+                                     "vs float64 equal to plain fp32)"}.get(args.engine, "fp32"),
             "data": "synthetic", "config": {**workload_config(n_rays), "frames_per_step": fps,
-                                            "parallelism": f"block-cyclic ray-shard x{world} + all_gather",
+                                            "parallelism": (f"whole-frame shard x{world} + all_gather" if by_frame else
+                                                            f"block-cyclic ray-shard x{world} + all_gather"),
                                             "mlp_engine": args.engine,
                                             "skip_dead_samples": not args.all_samples},
             "e2e": {"value": e2e_val, "unit": "rays/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": bo, "d2h_bytes_per_step": bi,
                     "api": "neumesh_b200.volume_render on pinned host rays; rgb + depth read back to pinned host"},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kern,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_secondary": secondary,
+            "kernels": kern,
             "all_samples": {"value": n_rays * args.steps / (ms_all * 1e-3), "unit": "rays/s",
                             "ms_per_step": ms_all / args.steps,
                             "note": "same frames with colour / nabla evaluated at EVERY sample as the reference does "

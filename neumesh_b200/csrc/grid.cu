@@ -394,10 +394,16 @@ static int build_grid(const float* vertices, int64_t V, cudaStream_t stream, nmb
                                                                                nlast.p, g->pts.p, g->nodes.p);
     NMB_LAUNCH_OK();
   }
-  // directory tables: levels [3, min(L - 1, 7)] (finer cells than the vertex spacing buy nothing)
+  // directory tables: levels [3, min(L - 1, 7)] (finer cells than the vertex spacing buy nothing).  OPT-IN
+  // (NMB_KNN_DIR=1): measured on B200 the directory start is bit-identical but not faster (knn 130.2 -> 133.7 ms, live
+  // lists 43.4 -> 48.3 ms per 800x800 frame, profiles/r2_knn_directory_ab.txt): with a warm bound the ball meets only 1-2
+  // children per TOP level, so the levels it skips cost about as much as the 2x2x2-cell seeding does; the expansions that
+  // dominate a walk sit at the bottom levels, where cells are as small as the ball.
   g->dir_lmin = 3;
   g->dir_lmax = std::min(L - 1, 7);
   if (getenv("NMB_KNN_DIR_MAX")) g->dir_lmax = std::min(g->dir_lmax, atoi(getenv("NMB_KNN_DIR_MAX")));
+  static const bool want_dir = getenv("NMB_KNN_DIR") != nullptr || getenv("NMB_KNN_COOP") != nullptr;
+  if (!want_dir) g->dir_lmax = g->dir_lmin - 1;
   if (g->dir_lmax >= g->dir_lmin) {
     int64_t total = 0;
     int32_t offs[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -75,6 +75,28 @@ def gather_image(part: dict, n_rays: int, rank: int, world: int) -> "OrderedDict
     return out
 
 
+def gather_image_contiguous(part: dict, world: int) -> "OrderedDict[str, torch.Tensor]":
+    """As ``gather_image`` when every rank rendered an equally long CONTIGUOUS slice of the ray list (whole frames of a
+    multi-frame step): rank r's rows land at [r * n, (r + 1) * n) - one ``all_gather_into_tensor``, no re-ordering."""
+    keys = [(k, c) for k, c in PACK_KEYS if k in part]
+    width = sum(c for _, c in keys)
+    ref = part[keys[0][0]]
+    n = ref.shape[0]
+    tile = torch.cat([part[k].reshape(n, c) for k, c in keys], dim=1).contiguous()
+    if world == 1 or not dist.is_initialized():
+        flat = tile
+    else:
+        flat = torch.empty(world * n, width, dtype=torch.float32, device=ref.device)
+        dist.all_gather_into_tensor(flat, tile)
+    out = OrderedDict()
+    col = 0
+    for k, c in keys:
+        v = flat[:, col:col + c]
+        out[k] = v.reshape(-1).contiguous() if c == 1 else v.contiguous()
+        col += c
+    return out
+
+
 def render_sharded(rays_o, rays_d, model, **render_kwargs):
     """Render this rank's slice with the fused path and all-gather the image.  Single process: plain render."""
     from .renderer import render_fused
