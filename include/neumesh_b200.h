@@ -180,6 +180,14 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
 int nmb_upsample_step(const float* z, const float* sdf, int64_t N, int32_t n, int32_t n_new, float inv_s,
                       float* z_new, float* scratch, void* stream);
 
+/* Surface rendering by root finding (models/ray_casting.py:45-200, dead code in the reference but part of the named
+ * path): given the field values val [N, n_steps] at the linspace(near, far, n_steps) proposals of every ray, the bracket
+ * of the FIRST sign change of val - tau (models/ray_casting.py:96-160): d_high / f_high at the proposal before it, d_low /
+ * f_low after it; mask = change && positive-to-negative && first proposal not occupied (uint8). */
+int nmb_first_crossing(const float* val, int64_t N, int32_t n_steps, float tau, const float* near, const float* far,
+                       float* d_low, float* f_low, float* d_high, float* f_high, uint8_t* mask,
+                       uint8_t* mask_sign_change, uint8_t* first_free, void* stream);
+
 /* Ray generation (utils/rend_util.py:97-176 get_rays/lift, full image, no skew handling beyond K[0,1]).
  * c2w [3,4] or [4,4] row-major (first 3 rows used), intr = {fx, fy, cx, cy, skew}. rays_o, rays_d [H*W,3]. */
 int nmb_get_rays(const float* c2w_host /*HOST 12 floats*/, const float* intr_host /*HOST 5 floats*/, int32_t H,

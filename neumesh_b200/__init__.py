@@ -17,8 +17,9 @@ from .mesh_grid import GridHandle, MeshGrid, MeshPrimitive, frnn_grid_points  # 
 from .neumesh import Embedder, NeuMesh, get_embedder, interpolation  # noqa: F401
 from .renderer import SingleRenderer, release_workspace, volume_render  # noqa: F401
 from .texture_neumesh import TextureEditableNeuMesh  # noqa: F401
+from .neus import NeuS  # noqa: F401
 from . import parallel  # noqa: F401
 
 __all__ = ["NeuMesh", "MeshGrid", "MeshPrimitive", "GridHandle", "frnn_grid_points", "volume_render",
            "release_workspace", "TextureEditableNeuMesh", "SingleRenderer", "Embedder", "get_embedder",
-           "interpolation", "parallel"]
+           "interpolation", "parallel", "NeuS"]

@@ -70,6 +70,7 @@ SIGNATURES = {
     "nmb_render": (C.c_int, [_P, C.POINTER(RenderCfg), _P, _P, _I64, _I64, _P, _P, _P, _P, C.POINTER(RenderDetail),
                              _P, _I64, _P]),
     "nmb_upsample_step": (C.c_int, [_P, _P, _I64, _I32, _I32, _F, _P, _P, _P]),
+    "nmb_first_crossing": (C.c_int, [_P, _I64, _I32, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nmb_pack_bgr8": (C.c_int, [_P, _I64, _P, _P]),
     "nmb_vertex_normals": (C.c_int, [_P, _I64, _P, _I64, _P, _P]),
     "nmb_get_rays": (C.c_int, [C.POINTER(_F), C.POINTER(_F), _I32, _I32, _P, _P, _P]),

@@ -502,6 +502,44 @@ __global__ void pack_bgr8_kernel(const float* __restrict__ rgb, int64_t N, uint8
   }
 }
 
+// models/ray_casting.py:96-160 (root_finding_surface_points): per ray, the first sign change of val - tau along the
+// N_steps proposals; kept only if it goes from positive (outside) to negative (inside) and the first proposal is not
+// occupied.  Outputs the bracket of the secant search.  val is row-major [N, n_steps].
+__global__ void first_crossing_kernel(int64_t N, int n_steps, float tau, const float* __restrict__ val,
+                                      const float* __restrict__ near, const float* __restrict__ far,
+                                      float* __restrict__ d_low, float* __restrict__ f_low, float* __restrict__ d_high,
+                                      float* __restrict__ f_high, uint8_t* __restrict__ mask,
+                                      uint8_t* __restrict__ mask_sign_change, uint8_t* __restrict__ first_free) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (r >= N) return;
+  const float* v = val + r * n_steps;
+  const float v0 = v[0] - tau;
+  int idx = -1;
+  float prev = v0;
+  for (int i = 0; i + 1 < n_steps; ++i) {
+    const float cur = v[i + 1] - tau;
+    if (prev * cur < 0.f) {   // torch.sign(val[i] * val[i+1]) == -1: the minimum of sign * (N_steps - i) picks the first
+      idx = i;
+      break;
+    }
+    prev = cur;
+  }
+  const bool change = idx >= 0;
+  const bool pos_to_neg = change && (v[idx] - tau) > 0.f;
+  const bool free0 = v0 > 0.f;
+  const bool m = change && pos_to_neg && free0;
+  mask[r] = m ? 1 : 0;
+  mask_sign_change[r] = change ? 1 : 0;
+  first_free[r] = free0 ? 1 : 0;
+  const int i0 = change ? idx : 0, i1 = change ? min(idx + 1, n_steps - 1) : 0;
+  const float n = near[r], f = far[r];
+  const float t0 = linspace01(i0, n_steps), t1 = linspace01(i1, n_steps);
+  d_high[r] = __fadd_rn(__fmul_rn(n, __fsub_rn(1.0f, t0)), __fmul_rn(f, t0));   // the proposal BEFORE the crossing
+  f_high[r] = v[i0] - tau;
+  d_low[r] = __fadd_rn(__fmul_rn(n, __fsub_rn(1.0f, t1)), __fmul_rn(f, t1));
+  f_low[r] = v[i1] - tau;
+}
+
 __global__ void face_normals_kernel(const float* __restrict__ v, const int32_t* __restrict__ tri, int64_t T,
                                     float* __restrict__ acc) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -836,6 +874,18 @@ int nmb_upsample_step(const float* z, const float* sdf, int64_t N, int32_t n, in
   if (N <= 0) return 0;
   nmb::upsample_kernel<<<(unsigned)nmb::ceil_div(N, nmb::RT), nmb::RT, 0, static_cast<cudaStream_t>(stream)>>>(
       N, n, n_new, inv_s, z, sdf, scratch, z_new, nullptr, 0, nullptr);
+  NMB_LAUNCH_OK();
+  return 0;
+}
+
+int nmb_first_crossing(const float* val, int64_t N, int32_t n_steps, float tau, const float* near, const float* far,
+                       float* d_low, float* f_low, float* d_high, float* f_high, uint8_t* mask,
+                       uint8_t* mask_sign_change, uint8_t* first_free, void* stream) {
+  NMB_CHECK(val && near && far && d_low && f_low && d_high && f_high && mask && mask_sign_change && first_free && n_steps >= 2,
+            "bad argument");
+  if (N <= 0) return 0;
+  nmb::first_crossing_kernel<<<(unsigned)nmb::ceil_div(N, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      N, n_steps, tau, val, near, far, d_low, f_low, d_high, f_high, mask, mask_sign_change, first_free);
   NMB_LAUNCH_OK();
   return 0;
 }

@@ -147,7 +147,61 @@ def make_texture_case(name, seed):
     print("wrote", path, os.path.getsize(path), "bytes; points recoloured by the edit:", int(changed.sum()), "of 500")
 
 
+def make_neus_case(name, seed):
+    """Point outputs of the UNMODIFIED NeuS teacher (models/frameworks/neus/neus.py + models/base.py)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import contextlib
+    import io
+    import helpers
+    ns = ref_harness.load()
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = ns.neus.NeuS(**helpers.NEUS_KW)
+    sd = helpers.neus_state_dict(model, seed)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    torch.manual_seed(seed)
+    x = (torch.rand(700, 3) * 2 - 1) * 0.8
+    v = torch.nn.functional.normalize(torch.randn(700, 3), dim=-1)
+    with torch.no_grad():
+        sdf, rad = model.forward(x.clone(), v)
+        sdf2, nabla = model.forward_with_nablas(x.clone())
+        dens = model.forward_density_only(x)
+    out = dict(seed=np.int64(seed), keys=np.array(sorted(model.state_dict().keys())), state_digest=np.array(state_digest(sd)),
+               x=x.numpy(), view_dirs=v.numpy(), sdf=sdf.numpy(), radiance=rad.numpy(), nabla=nabla.numpy(),
+               density_only=dens.numpy())
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes; |sdf| max", float(sdf.abs().max()))
+
+
+def make_raycast_case(name, seed):
+    """``root_finding_surface_points`` / ``sphere_tracing_surface_points`` of the UNMODIFIED ``models/ray_casting.py`` over
+    the reference NeuMesh field."""
+    ns = ref_harness.load()
+    cfg = synth.ModelConfig()
+    mesh = synth.icosphere_mesh(4, seed=seed)
+    sd = synth.make_state_dict(mesh, cfg, seed=seed + 1)
+    model = ref_harness.build_reference_model(mesh, cfg, sd)
+    o, d = synth.frame_rays(20, 20, view=6)
+    d = torch.nn.functional.normalize(d, dim=-1)
+    fn = lambda x: model.forward_density_only(x).squeeze(-1)   # noqa: E731
+    with torch.no_grad():
+        dp, pt, mask, msc = ns.ray_casting.root_finding_surface_points(fn, o.clone(), d.clone(), near=1.5, far=3.5,
+                                                                        batched=False, N_steps=128, N_secant_steps=8)
+    out = dict(seed=np.int64(seed), state_digest=np.array(state_digest(sd)), rays_o=o.numpy(), rays_d=d.numpy(),
+               d_pred=dp.numpy(), pt_pred=pt.numpy(), mask=mask.numpy(), mask_sign_change=msc.numpy())
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes; rays hitting the surface:", int(mask.sum()), "of", mask.numel())
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "raycast":
+        make_raycast_case("ray_casting_small", seed=60)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "neus":
+        make_neus_case("neus_teacher_small", seed=50)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "texture":
         make_texture_case("texture_edit_small", seed=40)
         return
@@ -162,6 +216,8 @@ def main():
               dict(calc_normal=False, white_bkgd=False, bounded_near_far=False), seed=20)
     make_train_case("train_step_small", 3, 48, seed=30)
     make_texture_case("texture_edit_small", seed=40)
+    make_neus_case("neus_teacher_small", seed=50)
+    make_raycast_case("ray_casting_small", seed=60)
 
 
 if __name__ == "__main__":

@@ -71,6 +71,8 @@ def load():
         import utils.rend_util as rend_util
         import utils.train_util as train_util
         import editing.texture_neumesh.texture_neumesh as texture_neumesh   # empty package __init__: no Open3D import
+        import models.frameworks.neus.neus as neus
+        import models.ray_casting as ray_casting
     finally:
         sys.path.remove(REF_ROOT)
 
@@ -91,7 +93,7 @@ def load():
             return self.vertices.shape[0]
 
     ns = types.SimpleNamespace(renderer=renderer, mesh_grid=mesh_grid, base=base, neumesh=neumesh,
-                               rend_util=rend_util, train_util=train_util, texture_neumesh=texture_neumesh,
+                               rend_util=rend_util, train_util=train_util, texture_neumesh=texture_neumesh, neus=neus, ray_casting=ray_casting,
                                HarnessMeshGrid=HarnessMeshGrid)
     _loaded = ns
     return ns

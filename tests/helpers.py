@@ -126,3 +126,26 @@ def texture_edit_oracle(case, dtype=torch.float32):
     refs = [oracle_field(m, case["cfg"], sd, dtype) for m, sd in case["refs"]]
     rot = torch.stack([T[:3, :3] for T in case["T"]])
     return TextureEditOracle(main, refs, case["masks"], case["codes"], rot)
+
+
+NEUS_KW = dict(variance_init=0.05, speed_factor=10.0, W_geo_feat=256, obj_bounding_radius=1.0,
+               surface_cfg=dict(embed_multires=6, radius_init=0.5, geometric_init=True, D=8, W=256, skips=[4]),
+               radiance_cfg=dict(embed_multires=-1, embed_multires_view=4, use_view_dirs=True, D=4, W=256, skips=[]))
+
+
+def neus_state_dict(model, seed=50):
+    """Deterministic parameters for a NeuS teacher (reference or drop-in: same keys, same shapes), by key name.
+    A sphere-like sdf: the model's own geometric initialisation is kept for the structure, then perturbed."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k in sorted(model.state_dict()):
+        v = model.state_dict()[k]
+        if k.endswith("weight_v"):
+            sd[k] = torch.randn(v.shape, generator=g) / (v.shape[-1] ** 0.5)
+        elif k.endswith("weight_g"):
+            sd[k] = 0.8 + 0.4 * torch.rand(v.shape, generator=g)
+        elif k.endswith("bias"):
+            sd[k] = 0.05 * torch.randn(v.shape, generator=g)
+        else:
+            sd[k] = v.clone()
+    return sd
