@@ -309,8 +309,18 @@ def _render_from_samples(rays_o, rays_d, model, z_all, query, *, calc_normal, us
     else:
         view_dirs = rays_d if use_view_dirs else None
         dirs = view_dirs.unsqueeze(-2).expand_as(pts_mid)
-    sdf_mid, radiances = query(model.forward, pts_mid, dirs)
     w = alpha_to_w(alpha)
+    if not torch.is_grad_enabled() and not detailed_output and pts_mid.dim() == 3:
+        # live-sample evaluation (as csrc/render.cu does for a plain NeuMesh): colour is multiplied by the visibility
+        # weight below, so mid-points whose weight is exactly 0.0 are not evaluated - adding 0 * c is exact
+        live = w != 0
+        radiances = torch.zeros_like(pts_mid)
+        if bool(live.any()):
+            _, c_live = model.forward(pts_mid[live], dirs[live])
+            radiances[live] = c_live
+        sdf_mid = None
+    else:
+        sdf_mid, radiances = query(model.forward, pts_mid, dirs)
     rgb = (w[..., None] * radiances).sum(dim=-2)
     depth = (w / (w.sum(dim=-1, keepdim=True) + 1e-10) * z_mid).sum(dim=-1)
     acc = w.sum(dim=-1)
@@ -385,6 +395,20 @@ def volume_render(rays_o, rays_d, model, obj_bounding_radius=1.0, batched=False,
         return out["rgb"], out["depth_volume"], out
 
     rays_d = F.normalize(rays_d, dim=-1)
+    geo = getattr(model, "main_model", None)   # TextureEditableNeuMesh: geometry (and the cascade) is the main model's
+    if (isinstance(geo, NeuMesh) and not torch.is_grad_enabled() and z_samples is None and rays_o.is_cuda
+            and geo.fused_supported() and geo.geometry_features.is_cuda and use_view_dirs and not random_color_direction
+            and (not batched or rays_o.shape[0] == 1) and N_samples >= 2
+            and (N_upsample_iters == 0 or N_importance % max(N_upsample_iters, 1) == 0)):
+        # texture-edit render (editing/texture_neumesh/texture_renderer.py): fused sampling cascade on the main model's
+        # geometry; the colour blend of the edit runs per live sample through the fused field kernels
+        z_samples = render_fused(rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), geo, obj_bounding_radius=obj_bounding_radius,
+                                 near_bypass=near_bypass, far_bypass=far_bypass, N_samples=N_samples,
+                                 N_importance=N_importance, N_upsample_iters=N_upsample_iters,
+                                 bounded_near_far=bounded_near_far, normalize_dirs=False, min_chunk=rayschunk,
+                                 perturb=perturb, perturb_u=perturb_u, sampling_only=True)["d_all"]
+        if batched:
+            z_samples = z_samples.unsqueeze(0)
     if (isinstance(model, NeuMesh) and torch.is_grad_enabled() and z_samples is None and rays_o.is_cuda
             and model.fused_supported() and model.geometry_features.is_cuda and use_view_dirs
             and (not batched or rays_o.shape[0] == 1) and N_samples >= 2

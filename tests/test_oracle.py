@@ -92,3 +92,41 @@ def test_oracle_vs_unmodified_reference():
     bins = torch.sort(torch.rand(64, 40), dim=-1)[0]
     wts = torch.rand(64, 39) * (torch.rand(64, 39) > 0.5)
     assert torch.equal(ns.rend_util.sample_pdf(bins, wts, 16, det=True), orender.inverse_cdf_samples(bins, wts, 16))
+
+
+def test_reference_renderer_and_trainer_loss_run_on_the_dropin_model():
+    """INTEGRATION.md section 3 end to end, as far as a CPU allows: the UNMODIFIED ``models/renderer.py::volume_render``
+    drives the drop-in ``neumesh_b200.NeuMesh`` (its protocol is all the reference's renderer touches), no-grad and under
+    autograd with ``perturb=True``, and the result equals what the reference renders with its own model."""
+    import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference tree not present (GPU box)")
+    import neumesh_b200 as nb
+    ns = ref_harness.load()
+    cfg = synth.ModelConfig()
+    mesh = synth.icosphere_mesh(3, seed=5)
+    sd = synth.make_state_dict(mesh, cfg, seed=6)
+    ref = ref_harness.build_reference_model(mesh, cfg, sd)
+    ours = nb.NeuMesh(helpers.OracleMeshGrid(mesh), **cfg.model_kwargs())
+    ours.load_state_dict(sd, strict=True)      # identical state_dict keys
+    ours.eval()
+    o, d = synth.frame_rays(8, 8, view=2)
+    kw = dict(calc_normal=True, white_bkgd=True, bounded_near_far=True, detailed_output=True, rayschunk=64)
+    with torch.no_grad():
+        rgb_r, dep_r, ex_r = ns.renderer.volume_render(o, d, ref, **kw)
+        rgb_o, dep_o, ex_o = ns.renderer.volume_render(o, d, ours, **kw)          # reference renderer, drop-in model
+        rgb_n, dep_n, ex_n = nb.volume_render(o, d, ours, **kw)                   # drop-in renderer, drop-in model
+    assert set(ex_r.keys()) == set(ex_o.keys()) <= set(ex_n.keys()) | {"near_far"}
+    for a, b in ((rgb_o, rgb_r), (dep_o, dep_r), (rgb_n, rgb_r), (dep_n, dep_r)):
+        assert (a - b).abs().max() < 1e-5
+    # training-style call: grad enabled, perturb=True (the reference's default), samples_output for the distillation loss
+    ours.train()
+    ours.fused_train = False
+    torch.manual_seed(3)
+    rgb_t, dep_t, ex_t = ns.renderer.volume_render(o, d, ours, calc_normal=True, detailed_output=True, samples_output=True,
+                                                   perturb=True, rayschunk=64)
+    assert {"xyz", "dirs", "density", "colors", "implicit_nablas"} <= set(ex_t.keys())
+    loss = helpers.train_loss(rgb_t, dep_t, ex_t) + ex_t["density"].abs().mean() + ex_t["colors"].mean()
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for n, p in ours.named_parameters()
+               if n != "indicator_weight_raw")
