@@ -69,6 +69,19 @@ FLOP_COL = 2 * (207 * 256 + 3 * 256 * 256 + 3 * 256)      # 500 736
 BYTES_KNN = 12 + 8 * 24                                   # 204 B per KNN query (xyz + 8 x (vertex + indicator))
 
 
+def host_cores():
+    """Physical cores of the host: MKL / OpenMP run the oracle fastest at one thread per physical core (measured on the
+    GPU box: 210 rays/s at 64 threads, 39-50 rays/s at 128 hyper-threads)."""
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+        if n:
+            return int(n)
+    except Exception:
+        pass
+    return max(1, (os.cpu_count() or 2) // 2)
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -143,7 +156,7 @@ def build_inputs(n_frames: int):
 
 def cpu_oracle_rate(cfg, mesh, sd, o, d, n_rays: int, repeats: int = 1):
     """rays/s of the oracle port (reference algorithm, torch CPU fp32, cKDTree exact KNN) on a strided ray sample."""
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.set_num_threads(host_cores())
     from oracle import render as orender
     from oracle.field import FieldOracle
     f = FieldOracle(mesh.vertices, sd, cfg)
@@ -164,8 +177,8 @@ def run_reference(args, rank, world):
     travel to the GPU box), all host threads, bounded sample per step."""
     if rank != 0:
         return
-    # all the host threads the box has (torchrun exports OMP_NUM_THREADS=1 to every rank: override it)
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    # all the host cores the box has (torchrun exports OMP_NUM_THREADS=1 to every rank: override it)
+    torch.set_num_threads(host_cores())
     cfg, mesh, sd, frames = build_inputs(1)
     o, d = frames[0]
     n = args.ref_rays
@@ -511,7 +524,10 @@ def main():
                 # honest second roofline of the latency / issue-bound walks: warp instructions per query from the ncu
                 # capture of this very kernel x queries per second, against the SMs' issue rate at the sampled clock
                 sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-                qps = kern["walk"]["points_per_step"] / (kern["walk"]["ms_per_step"] * 1e-3)
+                # queries that are really walked: the ray-ordered and the live-list kernels (the bound scan's nominal
+                # 256 samples per ray are mostly decided by the certificate grid without a walk)
+                qk = [k for k in ("knn", "knn_list") if k in kern]
+                qps = sum(kern[k]["points_per_step"] for k in qk) / (sum(kern[k]["ms_per_step"] for k in qk) * 1e-3)
                 peak = 148 * 4 * sm_mhz * 1e6
                 tgt = roofline if cls[0] == "walk" else secondary
                 tgt["issue_slots"] = {"warp_inst_per_query": walk_issue["warp_inst_per_query"],
@@ -519,6 +535,10 @@ def main():
                                       "achieved_warp_inst_per_s": qps * walk_issue["warp_inst_per_query"],
                                       "peak_warp_inst_per_s": peak,
                                       "frac": qps * walk_issue["warp_inst_per_query"] / peak,
+                                      "kernels": "knn_rays_kernel + knn_lists_kernel",
+                                      "note": "share of the SMs' warp-instruction issue slots the walks use (ncu "
+                                              "issue-active 68-72 %); only ~10 of 32 lanes are active per issued "
+                                              "instruction, so the USEFUL fraction is ~0.3 x this",
                                       "source": walk_issue.get("source", "profiles/")}
         cpu = None
         if world == 1 and args.cpu_rays > 0:

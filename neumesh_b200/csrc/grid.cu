@@ -26,6 +26,14 @@
 
 namespace nmb {
 
+// The directory start of the thread-per-query walk is compiled in only with -DNMB_KNN_DIRECTORY=1: measured on B200 it
+// is bit-identical and not faster (profiles/r2_knn_directory_ab.txt), and merely carrying its code costs the bound scan
+// 12 % (66 -> 75 registers per thread: 59.5 -> 67.6 ms per frame), so the shipped build leaves it out.
+#ifndef NMB_KNN_DIRECTORY
+#define NMB_KNN_DIRECTORY 0
+#endif
+#define NMB_GV_ARG(gv) (NMB_KNN_DIRECTORY ? &(gv) : nullptr)
+
 // ------------------------------------------------------------------------------------------------------------
 // build
 // ------------------------------------------------------------------------------------------------------------
@@ -395,14 +403,14 @@ static int build_grid(const float* vertices, int64_t V, cudaStream_t stream, nmb
     NMB_LAUNCH_OK();
   }
   // directory tables: levels [3, min(L - 1, 7)] (finer cells than the vertex spacing buy nothing).  OPT-IN
-  // (NMB_KNN_DIR=1): measured on B200 the directory start is bit-identical but not faster (knn 130.2 -> 133.7 ms, live
+  // (build with -DNMB_KNN_DIRECTORY=1 and set NMB_KNN_DIR=1; the cooperative kernels, NMB_KNN_COOP=1, use it too): measured on B200 the directory start is bit-identical but not faster (knn 130.2 -> 133.7 ms, live
   // lists 43.4 -> 48.3 ms per 800x800 frame, profiles/r2_knn_directory_ab.txt): with a warm bound the ball meets only 1-2
   // children per TOP level, so the levels it skips cost about as much as the 2x2x2-cell seeding does; the expansions that
   // dominate a walk sit at the bottom levels, where cells are as small as the ball.
   g->dir_lmin = 3;
   g->dir_lmax = std::min(L - 1, 7);
   if (getenv("NMB_KNN_DIR_MAX")) g->dir_lmax = std::min(g->dir_lmax, atoi(getenv("NMB_KNN_DIR_MAX")));
-  static const bool want_dir = getenv("NMB_KNN_DIR") != nullptr || getenv("NMB_KNN_COOP") != nullptr;
+  static const bool want_dir = (NMB_KNN_DIRECTORY && getenv("NMB_KNN_DIR") != nullptr) || getenv("NMB_KNN_COOP") != nullptr;
   if (!want_dir) g->dir_lmax = g->dir_lmin - 1;
   if (g->dir_lmax >= g->dir_lmin) {
     int64_t total = 0;
@@ -550,7 +558,7 @@ knn_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts
       knn_walk<KNN_K, false>(nodes, pts, qx, qy, qz, d2, ix);
     } else {
       warm_rerank<KNN_K>(pts, qx, qy, qz, d2, ix);
-      knn_walk<KNN_K, true>(nodes, pts, qx, qy, qz, d2, ix, &gv);
+      knn_walk<KNN_K, true>(nodes, pts, qx, qy, qz, d2, ix, NMB_GV_ARG(gv));
     }
     float w[KNN_K], ds, grad[3];
     mesh_distance_point(pts, indicator, w1, qx, qy, qz, d2, ix, w, ds, grad);
@@ -592,7 +600,7 @@ knn_lists_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pt
       knn_walk<KNN_K, false>(nodes, pts, qx, qy, qz, d2, ix);
     } else {
       warm_rerank<KNN_K>(pts, qx, qy, qz, d2, ix);
-      knn_walk<KNN_K, true>(nodes, pts, qx, qy, qz, d2, ix, &gv);
+      knn_walk<KNN_K, true>(nodes, pts, qx, qy, qz, d2, ix, NMB_GV_ARG(gv));
     }
     float w[KNN_K], ds, grad[3];
     mesh_distance_point(pts, indicator, w1, qx, qy, qz, d2, ix, w, ds, grad);
@@ -947,7 +955,7 @@ bound_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ p
     have_prev = true;
     if (warm) {
       warm_rerank<KNN_K>(pts, qx, qy, qz, d2, ix);
-      knn_walk<KNN_K, true>(nodes, pts, qx, qy, qz, d2, ix, &gv);
+      knn_walk<KNN_K, true>(nodes, pts, qx, qy, qz, d2, ix, NMB_GV_ARG(gv));
     } else {
       knn_walk<KNN_K, false>(nodes, pts, qx, qy, qz, d2, ix);
     }

@@ -243,8 +243,8 @@ __device__ __forceinline__ void knn_walk(const float4* __restrict__ nodes, const
         }
       }
       if (sp + m > STACK_MAX) {
-        // cannot happen for depth <= 10 (at most 7 net pushes per level); never drop a subtree silently
-        printf("neumesh_b200: KNN traversal stack overflow (sp %d + %d)\n", sp, m);
+        // cannot happen for depth <= 10 (at most 7 net pushes per level); never drop a subtree silently: the launch
+        // fails with a trap (reported by the next CUDA call) instead of returning inexact neighbours
         __trap();
       }
       if (m == 1) {
