@@ -533,7 +533,7 @@ knn_distance_kernel(const float4* __restrict__ nodes, const float4* __restrict__
 // Ray-ordered variant: one thread per RAY walks its S samples in depth order and warm-starts every query with the
 // previous sample's neighbours (consecutive samples are <~0.03 apart, so the initial 8th-best bound is already within
 // a few percent of the final one and the octree walk prunes almost everything).  A warp = 32 neighbouring rays.
-template <int MINB>
+template <int MINB, int ORDER>
 __global__ void __launch_bounds__(128, MINB)
 knn_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts, const float4* __restrict__ indicator,
                 float w1, PointSrc src, int S, int seg, KnnOut out, const GridView gv) {
@@ -555,10 +555,10 @@ knn_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts
     const float qy = __fadd_rn(oy, __fmul_rn(z, dy));
     const float qz = __fadd_rn(oz, __fmul_rn(z, dz));
     if (s == s_begin) {
-      knn_walk<KNN_K, false>(nodes, pts, qx, qy, qz, d2, ix);
+      knn_walk<KNN_K, false, ORDER>(nodes, pts, qx, qy, qz, d2, ix);
     } else {
       warm_rerank<KNN_K>(pts, qx, qy, qz, d2, ix);
-      knn_walk<KNN_K, true>(nodes, pts, qx, qy, qz, d2, ix, NMB_GV_ARG(gv));
+      knn_walk<KNN_K, true, ORDER>(nodes, pts, qx, qy, qz, d2, ix, NMB_GV_ARG(gv));
     }
     float w[KNN_K], ds, grad[3];
     mesh_distance_point(pts, indicator, w1, qx, qy, qz, d2, ix, w, ds, grad);
@@ -857,17 +857,19 @@ int launch_knn_distance(const nmb_grid* g, const float4* indicator_sorted, float
   }
   if (!src.xyz && src.R >= RAY_KERNEL_MIN_RAYS && P % src.R == 0) {
     const int S = (int)(P / src.R);
-    // segments per ray: enough threads to fill the GPU (~2 waves of 1024 threads per SM), at least 8 samples each
-    int64_t nseg = ceil_div((int64_t)sm_count() * 2048 * 2, src.R);
+    // segments per ray: enough threads for ~2 waves of the 1280 resident threads per SM (10 blocks of 128), at least 8
+    // samples each - every segment starts with a cold walk, so no more segments than the occupancy needs
+    int64_t nseg = ceil_div((int64_t)sm_count() * 1280 * 2, src.R);
     nseg = std::max<int64_t>(1, std::min<int64_t>(nseg, ceil_div(S, 8)));
     const int seg = (int)ceil_div(S, nseg);
     nseg = ceil_div(S, seg);
     static const int minb = getenv("NMB_KNN_MINB") ? atoi(getenv("NMB_KNN_MINB")) : 10;
     const GridView gv = make_view(g);
+    static const int order = getenv("NMB_KNN_ORDER") ? atoi(getenv("NMB_KNN_ORDER")) : 1;   // 0 = full child sort (A/B)
     const unsigned gridn = (unsigned)ceil_div(src.R * nseg, 128);
-    if (minb >= 12) knn_rays_kernel<12><<<gridn, 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src, S, seg, out, gv);
-    else if (minb >= 10) knn_rays_kernel<10><<<gridn, 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src, S, seg, out, gv);
-    else knn_rays_kernel<8><<<gridn, 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src, S, seg, out, gv);
+    if (minb >= 12) { if (order) knn_rays_kernel<12, 1><<<gridn, 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src, S, seg, out, gv); else knn_rays_kernel<12, 0><<<gridn, 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src, S, seg, out, gv); }
+    else if (minb >= 10) { if (order) knn_rays_kernel<10, 1><<<gridn, 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src, S, seg, out, gv); else knn_rays_kernel<10, 0><<<gridn, 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src, S, seg, out, gv); }
+    else { if (order) knn_rays_kernel<8, 1><<<gridn, 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src, S, seg, out, gv); else knn_rays_kernel<8, 0><<<gridn, 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1, src, S, seg, out, gv); }
     NMB_LAUNCH_OK();
     return 0;
   }

@@ -725,6 +725,42 @@ def test_config5_large_mesh_256_samples_per_ray():
     # free-running parity of this config against the unmodified reference: test_frame_parity_vs_reference_noise_floor
 
 
+def test_perturb_with_injected_uniforms_vs_oracle(case5):
+    """perturb=True on the fused path (``nmb_render_cfg.perturb_u``): the CUDA cascade with injected uniforms against the
+    oracle rendering with the SAME draws (the oracle's ``perturb_u`` path is pinned bit for bit to the unmodified
+    reference with a patched ``torch.rand``, tests/test_oracle.py).  Sample sets: the cascade's first iteration sees
+    identical inputs, so its new depths must agree to rounding on (almost) every ray; composited outputs: the usual
+    noise-floor bound."""
+    import neumesh_b200 as nb
+    from neumesh_b200.renderer import render_fused
+    from oracle import render as orender
+    mesh, cfg, sd, f = case5
+    dev = _dev()
+    model = helpers.cuda_model(mesh, cfg, sd)
+    o, d = synth.frame_rays(30, 30, view=3)
+    u = torch.rand(4, o.shape[0], 16, generator=torch.Generator().manual_seed(5))
+    kw = dict(calc_normal=True, white_bkgd=True, bounded_near_far=True)
+    with torch.no_grad():
+        rgb, depth, ex = nb.volume_render(o.to(dev), d.to(dev), model, detailed_output=False, perturb=True,
+                                          perturb_u=u.to(dev), **kw)
+        z = render_fused(o.to(dev), d.to(dev), model, perturb_u=u[:1].to(dev), sampling_only=True, N_importance=16,
+                         N_upsample_iters=1, **{k: v for k, v in kw.items() if k == "bounded_near_far"})["d_all"].cpu()
+    rgb_o, dep_o, ex_o = orender.volume_render(o, d, f, detailed_output=True, perturb_u=u, **kw)
+    _, _, ex_1 = orender.volume_render(o, d, f, detailed_output=True, perturb_u=u[:1], N_importance=16, N_upsample_iters=1, **kw)
+    dz = (z - ex_1["d_all"]).abs().max(-1)[0]
+    print(f"perturb: first-iteration sample sets: rays with max |dz| > 1e-5: {(dz > 1e-5).float().mean():.4f}, median {dz.median():.1e}")
+    assert (dz > 1e-5).float().mean() < 0.02
+    dr = (rgb.cpu() - rgb_o).abs().max(-1)[0]
+    dd = (depth.cpu() - dep_o).abs()
+    out = 1.0 - ((dr <= RGB_TOL) & (dd <= DEPTH_TOL)).float().mean().item()
+    print(f"perturb: rays outside (1e-4, 1e-5) of the oracle with the same draws: {out:.4f}")
+    assert out <= outlier_bound(REF_FLOOR["config1"], dr.numel()) and dr.median() <= 1e-6
+    # the draws matter: the deterministic render differs
+    with torch.no_grad():
+        rgb_det, _, _ = nb.volume_render(o.to(dev), d.to(dev), model, detailed_output=False, **kw)
+    assert not torch.equal(rgb_det, rgb)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # frame-scale free-running parity against the UNMODIFIED reference, with the reference's own noise floor as the bar
 # ---------------------------------------------------------------------------------------------------------------

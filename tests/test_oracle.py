@@ -130,3 +130,41 @@ def test_reference_renderer_and_trainer_loss_run_on_the_dropin_model():
     loss.backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for n, p in ours.named_parameters()
                if n != "indicator_weight_raw")
+
+
+def test_oracle_perturb_with_injected_uniforms_equals_reference_with_patched_rand():
+    """perturb=True (rend_util.py:292-295) draws ``torch.rand`` once per up-sampling iteration; the oracle takes the draws
+    as ``perturb_u``.  With ``torch.rand`` patched to hand the reference the same draws, both renders are bit-identical."""
+    import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference tree not present (GPU box)")
+    ns = ref_harness.load()
+    cfg = synth.ModelConfig()
+    mesh = synth.icosphere_mesh(3, seed=5)
+    sd = synth.make_state_dict(mesh, cfg, seed=6)
+    ref = ref_harness.build_reference_model(mesh, cfg, sd)
+    f = helpers.oracle_field(mesh, cfg, sd)
+    o, d = synth.frame_rays(9, 9, view=4)
+    u = torch.rand(4, o.shape[0], 16, generator=torch.Generator().manual_seed(11))
+    calls = {"n": 0}
+    real_rand = torch.rand
+
+    def fake_rand(*shape, **kw):
+        shp = tuple(shape[0]) if len(shape) == 1 and isinstance(shape[0], (list, tuple)) else tuple(shape)
+        out = u[calls["n"]].reshape(shp).clone()
+        calls["n"] += 1
+        return out
+
+    kw = dict(calc_normal=True, white_bkgd=False, bounded_near_far=True)
+    torch.rand = fake_rand
+    try:
+        with torch.no_grad():
+            rgb_r, dep_r, ex_r = ns.renderer.volume_render(o, d, ref, detailed_output=True, perturb=True, rayschunk=4096, **kw)
+    finally:
+        torch.rand = real_rand
+    assert calls["n"] == 4
+    rgb_o, dep_o, ex_o = orender.volume_render(o, d, f, detailed_output=True, perturb_u=u, **kw)
+    assert torch.equal(rgb_r, rgb_o) and torch.equal(dep_r, dep_o) and torch.equal(ex_r["d_final"], ex_o["d_final"])
+    # and it differs from the deterministic render (the draws are used)
+    rgb_d, _, _ = orender.volume_render(o, d, f, **kw)
+    assert not torch.equal(rgb_d, rgb_o)
