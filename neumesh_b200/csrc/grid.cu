@@ -824,7 +824,11 @@ int launch_knn_lists(const nmb_grid* g, const float4* indicator_sorted, float w1
     NMB_LAUNCH_OK();
     return 0;
   }
-  const int seg = 16;
+  // entries per thread: 16 when there is plenty of work (one cold walk per 16 queries); shorter segments when the lists
+  // of a small shard (multi-GPU single-frame mode) would leave the GPU under-filled - only rays that hit the object have
+  // entries at all, so the number of busy threads is ~M / seg, which should cover ~2 waves of the resident threads
+  int seg = 16;
+  while (seg > 4 && M / seg < (int64_t)sm_count() * 1280 * 2) seg >>= 1;
   const int max_seg = (int)ceil_div(max_list, seg);
   knn_lists_kernel<<<(unsigned)ceil_div(R * max_seg, 128), 128, 0, stream>>>(g->nodes.p, g->pts.p, indicator_sorted, w1,
                                                                             xyz, off, cnt, R, seg, max_seg, out,
@@ -1082,11 +1086,10 @@ knn_generic_kernel(const float4* __restrict__ nodes, const float4* __restrict__ 
             best = c;
           }
         if (best < 0) break;
-        if (sp < STACK_MAX) {
-          sn[sp] = link + best;
-          sd[sp] = bv;
-          ++sp;
-        }
+        if (sp >= STACK_MAX) __trap();   // cannot happen for depth <= 10; never drop a subtree silently
+        sn[sp] = link + best;
+        sd[sp] = bv;
+        ++sp;
         cd[best] = -1.f;
       }
     }

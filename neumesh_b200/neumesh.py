@@ -259,6 +259,10 @@ class NeuMesh(nn.Module):
         from . import train_ops
         lead = xyz.shape[:-1]
         flat = xyz.detach().reshape(-1, 3).float().contiguous()
+        if flat.shape[0] == 0:   # nothing to evaluate (empty shard): empty outputs, no kernel launch
+            z = flat.new_zeros(*lead, 1)
+            return z, flat.new_zeros(*lead, 3), (flat.new_zeros(*lead, 3) if with_color else None), \
+                (flat.new_zeros(*lead, 8, dtype=torch.int64), flat.new_zeros(*lead, 8))
         dirs = (view_dirs.detach().reshape(-1, 3).float().contiguous() if view_dirs is not None
                 else torch.zeros_like(flat))
         w1_t = self.forward_indicator_weight().reshape(()) if self.learn_indicator_weight else \
