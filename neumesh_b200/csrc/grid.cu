@@ -861,10 +861,10 @@ int launch_knn_distance(const nmb_grid* g, const float4* indicator_sorted, float
   }
   if (!src.xyz && src.R >= RAY_KERNEL_MIN_RAYS && P % src.R == 0) {
     const int S = (int)(P / src.R);
-    // segments per ray: enough threads for ~2 waves of the 1280 resident threads per SM (10 blocks of 128), at least 8
-    // samples each - every segment starts with a cold walk, so no more segments than the occupancy needs
+    // segments per ray: enough threads for ~2 waves of the 1280 resident threads per SM (10 blocks of 128) - every segment
+    // starts with a cold walk, so no more segments than the occupancy needs
     int64_t nseg = ceil_div((int64_t)sm_count() * 1280 * 2, src.R);
-    nseg = std::max<int64_t>(1, std::min<int64_t>(nseg, ceil_div(S, 8)));
+    nseg = std::max<int64_t>(1, std::min<int64_t>(nseg, ceil_div(S, 4)));   // at least 4 samples per segment
     const int seg = (int)ceil_div(S, nseg);
     nseg = ceil_div(S, seg);
     static const int minb = getenv("NMB_KNN_MINB") ? atoi(getenv("NMB_KNN_MINB")) : 10;

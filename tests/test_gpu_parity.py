@@ -748,8 +748,28 @@ def test_perturb_with_injected_uniforms_vs_oracle(case5):
     rgb_o, dep_o, ex_o = orender.volume_render(o, d, f, detailed_output=True, perturb_u=u, **kw)
     _, _, ex_1 = orender.volume_render(o, d, f, detailed_output=True, perturb_u=u[:1], N_importance=16, N_upsample_iters=1, **kw)
     dz = (z - ex_1["d_all"]).abs().max(-1)[0]
-    print(f"perturb: first-iteration sample sets: rays with max |dz| > 1e-5: {(dz > 1e-5).float().mean():.4f}, median {dz.median():.1e}")
-    assert (dz > 1e-5).float().mean() < 0.02
+    # An inverse-CDF sample that lands in a low-probability bin is ill-conditioned (dz = d cdf / density): a 1e-6 sdf
+    # difference moves it visibly.  The yardstick is again the reference arithmetic itself: the oracle with its sdf
+    # perturbed by sigma = 4e-7 (same draws).
+
+    class Noisy:
+        def __init__(self, base):
+            self.b, self.g = base, torch.Generator().manual_seed(9)
+
+        def __getattr__(self, k):
+            return getattr(self.b, k)
+
+        def forward_density_only(self, x):
+            y = self.b.forward_density_only(x)
+            return y + 4e-7 * torch.randn(y.shape, generator=self.g)
+
+    _, _, ex_n = orender.volume_render(o, d, Noisy(f), detailed_output=True, perturb_u=u[:1], N_importance=16,
+                                       N_upsample_iters=1, **kw)
+    dz_n = (ex_n["d_all"] - ex_1["d_all"]).abs().max(-1)[0]
+    moved, moved_n = (dz > 1e-5).float().mean().item(), (dz_n > 1e-5).float().mean().item()
+    print(f"perturb: first-iteration sample sets: rays with max |dz| > 1e-5: CUDA {moved:.4f}, oracle self-noise {moved_n:.4f}; "
+          f"median {dz.median():.1e}")
+    assert dz.median() <= 1e-6 and moved <= outlier_bound(max(moved_n, 0.01), dz.numel())
     dr = (rgb.cpu() - rgb_o).abs().max(-1)[0]
     dd = (depth.cpu() - dep_o).abs()
     out = 1.0 - ((dr <= RGB_TOL) & (dd <= DEPTH_TOL)).float().mean().item()
