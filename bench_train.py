@@ -21,6 +21,58 @@ N_RAYS = 512
 KW = dict(calc_normal=True, white_bkgd=False, bounded_near_far=True, detailed_output=True, perturb=True)
 
 
+def run_reference(args, world):
+    """CPU arm of the training workload: the reference's training-step arithmetic (torch autograd through the generic
+    renderer and the torch-op field, exact KNN by the oracle) on the host cores, on a bounded sample of rays per step."""
+    import time
+    import torch.nn.functional as F
+    import bench
+    import neumesh_b200 as nb
+    from neumesh_b200 import synth
+    from oracle.mesh_grid import OracleMeshGrid
+    torch.set_num_threads(bench.host_cores())
+    n = 64
+    cfg = synth.ModelConfig()
+    mesh = synth.icosphere_mesh(7, seed=0)
+    sd = synth.make_state_dict(mesh, cfg, seed=1)
+    model = nb.NeuMesh(OracleMeshGrid(mesh), **cfg.model_kwargs())
+    model.load_state_dict(sd)
+    model.train()
+    model.fused_train = False            # plain torch autograd on the CPU: the reference's own arithmetic
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+    normals0 = model.mesh_grid.get_vertex_normal_torch().detach().clone()
+    g = torch.Generator().manual_seed(1234)
+
+    def step(i):
+        o, d = synth.frame_rays(800, 800, view=i % 90)
+        sel = torch.randint(0, o.shape[0], (n,), generator=g)
+        tgt, msk = torch.rand(n, 3, generator=g), (torch.rand(n, generator=g) > 0.5).float()
+        opt.zero_grad(set_to_none=True)
+        rgb, depth, ex = nb.volume_render(o[sel], d[sel], model, rayschunk=4096, **KW)
+        nab_norm = ex["implicit_nablas"].norm(dim=-1)
+        acc = ex["mask_volume"].clamp(1e-3, 1 - 1e-3)
+        loss = F.l1_loss(rgb, tgt) + 0.1 * F.mse_loss(nab_norm, torch.ones_like(nab_norm)) \
+            + 0.1 * F.binary_cross_entropy(acc, msk) + 0.01 * F.mse_loss(model.indicator_vector, normals0)
+        loss.backward()
+        opt.step()
+
+    step(0)      # builds the kd-tree, warms MKL
+    t = time.perf_counter()
+    for i in range(args.steps):
+        step(1 + i)
+    dt = time.perf_counter() - t
+    val = n * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "train_rays_per_sec_512_rays_per_gpu", "value": val, "unit": "rays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "train_step_icosphere_V163842_F32_K8_512rays_per_gpu", "rays_per_step_sample": n},
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": bench.host_cores(), "kind": "port",
+                         "sample": f"{n} rays per step (torch CPU autograd through the generic renderer + torch-op field, "
+                                   f"oracle exact KNN), forward + backward + Adam"},
+        "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
 def main(args, rank, world, local_rank):
     import torch.distributed as dist
     import torch.nn.functional as F
@@ -30,9 +82,7 @@ def main(args, rank, world, local_rank):
 
     if args.impl == "reference":
         if rank == 0:
-            print(json.dumps({"impl": "reference", "unavailable": "the training step of the reference needs its Trainer, "
-                              "data loaders and a NeuS teacher checkpoint (not part of the hot path; no CPU baseline is "
-                              "timed for config 4)"}), flush=True)
+            run_reference(args, world)
         return
     assert torch.cuda.is_available(), "bench needs a CUDA device"
     torch.cuda.set_device(local_rank)

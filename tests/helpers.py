@@ -54,30 +54,7 @@ def sample_points(n, seed=0):
     return dirs * radii[:, None], view
 
 
-class OracleMeshGrid:
-    """TEST-ONLY stand-in for ``neumesh_b200.MeshGrid`` on CPU: same protocol, neighbour search by the oracle's exact
-    KNN.  Lets the differentiable torch-op path of ``neumesh_b200.NeuMesh`` / ``volume_render`` run without a GPU so
-    its gradients can be compared with the reference's autograd.  (The product has no CPU path.)"""
-
-    def __init__(self, mesh):
-        self.mesh = mesh
-        self.vertices = torch.as_tensor(np.asarray(mesh.vertices), dtype=torch.float32)
-        self.vertex_normals = torch.as_tensor(np.asarray(mesh.vertex_normals), dtype=torch.float32)
-        self.distance_method = "frnn"
-
-    def get_number_of_vertices(self):
-        return self.vertices.shape[0]
-
-    def get_vertex_normal_torch(self):
-        return self.vertex_normals
-
-    def get_vertices_torch(self):
-        return self.vertices
-
-    def compute_distance(self, xyz, indicator_vector=None, indicator_weight=0.1, K=8):
-        from oracle.field import mesh_distance
-        ind = self.vertex_normals if indicator_vector is None else indicator_vector
-        return mesh_distance(xyz, self.vertices, ind, indicator_weight, K)
+from oracle.mesh_grid import OracleMeshGrid  # noqa: E402,F401  (CPU stand-in for MeshGrid; test infrastructure)
 
 
 def train_loss(rgb, depth, extras):
