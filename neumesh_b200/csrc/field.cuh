@@ -74,7 +74,12 @@ struct FieldIn {
   const float* rays_d;    // [R,3]
   int64_t R;
   const float* color_table;   // colour only: [rows, Fc] table indexed by `slot` instead of the field's own (nullable)
+  const int32_t* index;       // geometry only (nullable): point p reads ds / slot / w / grad at position index[p] of the
+                              // SoA arrays instead of p (nmb_render: the live sample points re-use the neighbours found
+                              // in the sampling passes instead of walking the octree again); outputs are written at p
 };
+
+__device__ __forceinline__ int64_t field_src(const FieldIn& in, int64_t p) { return in.index ? (int64_t)in.index[p] : p; }
 
 // geometry: sdf [P]; if nabla != nullptr also nabla [3][P] (SoA, stride = in.stride)
 int launch_geo_ffma(const nmb_field* f, const FieldIn& in, int64_t P, float* sdf, float* nabla, cudaStream_t stream);

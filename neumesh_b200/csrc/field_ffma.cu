@@ -69,13 +69,14 @@ __global__ void __launch_bounds__(FT, 2) mlp_ffma_kernel(const FfmaParams prm) {
       const bool valid = p < prm.P;
       auto st = [&](int col, float v) { act[col * TM + m] = v; };
       if (valid) {
+        const int64_t ps = (MODE == 2) ? p : field_src(prm.in, p);   // where this point's neighbour data lives
         if (MODE == 1 && m >= 32) {
-          if (q == 0) store_scalar_pe_tangent(prm.in.ds[p], 0, L.Ld, st);
+          if (q == 0) store_scalar_pe_tangent(prm.in.ds[ps], 0, L.Ld, st);
         } else {
           float x[8];
-          blend8(MODE == 2 ? prm.tab.fc : prm.tab.fg, prm.in, p, q, x);
+          blend8(MODE == 2 ? prm.tab.fc : prm.tab.fg, prm.in, ps, q, x);
           store_feat_pe(x, q, MODE == 2 ? L.off_ft : L.off_fg, MODE == 2 ? L.Lft : L.Lfg, st);
-          if (q == 0) store_scalar_pe(prm.in.ds[p], 0, L.Ld, st);
+          if (q == 0) store_scalar_pe(prm.in.ds[ps], 0, L.Ld, st);
           if (MODE == 2 && q == 1) {
             float dx, dy, dz;
             load_dir(prm.in, p, dx, dy, dz);
@@ -194,9 +195,10 @@ __global__ void __launch_bounds__(FT, 2) mlp_ffma_kernel(const FfmaParams prm) {
         if (tid < 32 && p < prm.P) prm.out0[p] = s + prm.b_out[0];
         if (tid >= 32 && tid < 64 && p < prm.P && prm.out1) {
           // nabla = (d sdf / d ds) * grad_xyz ds
-          prm.out1[0 * prm.in.stride + p] = s * prm.in.grad[0 * prm.in.stride + p];
-          prm.out1[1 * prm.in.stride + p] = s * prm.in.grad[1 * prm.in.stride + p];
-          prm.out1[2 * prm.in.stride + p] = s * prm.in.grad[2 * prm.in.stride + p];
+          const int64_t ps = field_src(prm.in, p);
+          prm.out1[0 * prm.in.stride + p] = s * prm.in.grad[0 * prm.in.stride + ps];
+          prm.out1[1 * prm.in.stride + p] = s * prm.in.grad[1 * prm.in.stride + ps];
+          prm.out1[2 * prm.in.stride + p] = s * prm.in.grad[2 * prm.in.stride + ps];
         }
       }
     }

@@ -534,9 +534,10 @@ mlp_tc_kernel(const tc::Params prm) {
               } else if (MODE == 0 || r < 64) {
                 prm.out0[p] = o0 + __ldg(prm.b_out);
               } else if (prm.out1) {
-                prm.out1[0 * prm.in.stride + p] = o0 * prm.in.grad[0 * prm.in.stride + p];
-                prm.out1[1 * prm.in.stride + p] = o0 * prm.in.grad[1 * prm.in.stride + p];
-                prm.out1[2 * prm.in.stride + p] = o0 * prm.in.grad[2 * prm.in.stride + p];
+                const int64_t ps = field_src(prm.in, p);
+                prm.out1[0 * prm.in.stride + p] = o0 * prm.in.grad[0 * prm.in.stride + ps];
+                prm.out1[1 * prm.in.stride + p] = o0 * prm.in.grad[1 * prm.in.stride + ps];
+                prm.out1[2 * prm.in.stride + p] = o0 * prm.in.grad[2 * prm.in.stride + ps];
               }
             }
           }
@@ -581,15 +582,17 @@ mlp_tc_kernel(const tc::Params prm) {
       //      ring wait so that its latency overlaps the previous tile ----
       float feat[16];
       float ds = 0.f;
-      if (valid) ds = prm.in.ds[p];
+      // where this point's neighbour data lives (geometry modes: optionally indirected, see FieldIn::index)
+      const int64_t ps = (valid && MODE != 2) ? field_src(prm.in, p) : p;
+      if (valid) ds = prm.in.ds[ps];
       auto gather = [&](int fb) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) feat[i] = 0.f;
         if (valid && !tangent) {
 #pragma unroll
           for (int k = 0; k < KNN_K; ++k) {
-            const int32_t sl = prm.in.slot[k * prm.in.stride + p];
-            const float w = prm.in.w[k * prm.in.stride + p];
+            const int32_t sl = prm.in.slot[k * prm.in.stride + ps];
+            const float w = prm.in.w[k * prm.in.stride + ps];
             const float* row = table + (int64_t)sl * Fdim + fb * FEAT + 4 * h;
 #pragma unroll
             for (int g4 = 0; g4 < 4; ++g4) {

@@ -111,13 +111,14 @@ __global__ void bypass_kernel(int64_t R, int use_near, float nb, int use_far, fl
 
 // renderer.py:193-194: z[s][r] = near * (1 - t_s) + far * t_s
 __global__ void coarse_z_kernel(int64_t R, int S, const float* __restrict__ near, const float* __restrict__ far,
-                                float* __restrict__ z) {
+                                float* __restrict__ z, int32_t* __restrict__ origin) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= R * S) return;
   const int64_t r = i % R;
   const int s = (int)(i / R);
   const float t = linspace01(s, S);
   z[i] = __fadd_rn(__fmul_rn(near[r], __fsub_rn(1.0f, t)), __fmul_rn(far[r], t));
+  if (origin) origin[i] = s;   // sample s of ray r was evaluated as entry s of the neighbour arrays
 }
 
 // torch.sum over a contiguous fp32 row of n elements as ATen's CPU kernel computes it (SumKernel.cpp, the path
@@ -237,7 +238,9 @@ upsample_kernel(int64_t R, int n, int n_new, float inv_s, const float* __restric
 __global__ void __launch_bounds__(RT)
 merge_kernel(int64_t R, int n, int n_new, float* __restrict__ z, float* __restrict__ sdf,
              const float* __restrict__ znew, const float* __restrict__ sdfnew, float* __restrict__ nab,
-             const float* __restrict__ nabnew, int64_t nstride) {
+             const float* __restrict__ nabnew, int64_t nstride, int32_t* __restrict__ origin, int origin_new) {
+  // origin (nullable): [P][R] index of the evaluation pass entry a sample came from (the KNN results of every pass
+  // stay in place: entry e of ray r lives at position e * R + r); new sample b gets origin_new + b
   // nab / nabnew (nullable): [3][nstride] SoA payload (nabla at the samples) carried through the merge
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= R) return;
@@ -249,6 +252,7 @@ merge_kernel(int64_t R, int n, int n_new, float* __restrict__ z, float* __restri
       const int64_t src = (int64_t)a * R + r;
       z[dst] = za;
       sdf[dst] = sdf[src];
+      if (origin) origin[dst] = origin[src];
       if (nab) {
         nab[dst] = nab[src];
         nab[nstride + dst] = nab[nstride + src];
@@ -260,6 +264,7 @@ merge_kernel(int64_t R, int n, int n_new, float* __restrict__ z, float* __restri
       const int64_t src = (int64_t)b * R + r;
       z[dst] = zb;
       sdf[dst] = sdfnew[src];
+      if (origin) origin[dst] = origin_new + b;
       if (nab) {
         nab[dst] = nabnew[src];
         nab[nstride + dst] = nabnew[nstride + src];
@@ -370,7 +375,8 @@ __global__ void __launch_bounds__(RT)
 compact_live_kernel(int64_t R, int P, const int32_t* __restrict__ off, const float* __restrict__ wbuf,
                     const float* __restrict__ z, const float* __restrict__ zmid, const float* __restrict__ orig,
                     const float* __restrict__ dirs, float* __restrict__ xyz_mid, float* __restrict__ dir_live,
-                    float* __restrict__ xyz_pt /*nullable*/) {
+                    float* __restrict__ xyz_pt /*nullable*/, const int32_t* __restrict__ origin /*nullable*/,
+                    int32_t* __restrict__ live_src /*nullable: position of the live point's neighbour data*/) {
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= R) return;
   const float ox = orig[r * 3], oy = orig[r * 3 + 1], oz = orig[r * 3 + 2];
@@ -392,6 +398,7 @@ compact_live_kernel(int64_t R, int P, const int32_t* __restrict__ off, const flo
         xyz_pt[k * 3 + 1] = __fadd_rn(oy, __fmul_rn(zp, dy));
         xyz_pt[k * 3 + 2] = __fadd_rn(oz, __fmul_rn(zp, dz));
       }
+      if (live_src) live_src[k] = (int32_t)((int64_t)origin[q] * R + r);
       ++k;
     }
   }
@@ -401,7 +408,7 @@ compact_live_kernel(int64_t R, int P, const int32_t* __restrict__ off, const flo
 __global__ void __launch_bounds__(RT)
 composite_live_kernel(int64_t R, int P, int white_bkgd, const float* __restrict__ wbuf, const float* __restrict__ zmid,
                       const int32_t* __restrict__ off, const float* __restrict__ rgb_l /*[3][M]*/, int64_t M,
-                      const float* __restrict__ nabla_l /*[3][M] or null*/, const int32_t* __restrict__ perm,
+                      const float* __restrict__ nabla_l /*[3][Mn] or null*/, int64_t Mn, const int32_t* __restrict__ perm,
                       float* __restrict__ rgb_out, float* __restrict__ depth_out, float* __restrict__ acc_out,
                       float* __restrict__ normals_out) {
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -417,7 +424,7 @@ composite_live_kernel(int64_t R, int P, int white_bkgd, const float* __restrict_
       cg = __fadd_rn(cg, __fmul_rn(w, rgb_l[M + k]));
       cb = __fadd_rn(cb, __fmul_rn(w, rgb_l[2 * M + k]));
       if (nabla_l) {
-        const float gx = nabla_l[k], gy = nabla_l[M + k], gz = nabla_l[2 * M + k];
+        const float gx = nabla_l[k], gy = nabla_l[Mn + k], gz = nabla_l[2 * Mn + k];
         const float nn = fmaxf(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz))), 1e-12f);
         nx = __fadd_rn(nx, __fmul_rn(__fdiv_rn(gx, nn), w));
         ny = __fadd_rn(ny, __fmul_rn(__fdiv_rn(gy, nn), w));
@@ -583,6 +590,7 @@ struct Workspace {
   float *nabla_pts, *nabla_mid, *sdf_mid, *rgb;
   float *live_mid, *live_dir, *live_pt;   // [M,3] positions / directions of the live samples (M <= (P-1) R)
   int32_t *nlive, *live_off;
+  int32_t *origin, *live_src;             // [P][R] pass entry of every final sample; [M] neighbour-data position of a live point
   void* scan_tmp;
   int64_t scan_bytes;
   int64_t total;
@@ -623,6 +631,8 @@ Workspace carve(void* base, int64_t R, int P, int n_new) {
   w.live_pt = take(3 * PR);
   w.nlive = reinterpret_cast<int32_t*>(take(R));
   w.live_off = reinterpret_cast<int32_t*>(take(R + 1));
+  w.origin = reinterpret_cast<int32_t*>(take(PR));
+  w.live_src = reinterpret_cast<int32_t*>(take(PR));
   w.scan_bytes = 16 * 1024 + R / 32;   // cub::DeviceScan temp storage (a few KB; generous)
   w.scan_tmp = take(w.scan_bytes / 4 + 1);
   w.total = off;
@@ -713,12 +723,19 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
       NMB_LAUNCH_OK();
     }
     int n = cfg->N_samples;
-    coarse_z_kernel<<<(unsigned)ceil_div(R * n, 256), 256, 0, stream>>>(R, n, w.near, w.far, w.z);
+    // Live path with normals: the sample points whose visibility weight is non-zero need sdf' and the neighbours again
+    // at the end.  Every pass therefore leaves its KNN results in place (pass entry e of ray r at position e * R + r of
+    // the SoA arrays: coarse samples are entries 0..N_samples-1, iteration `it` adds N_samples + it * n_new ...) and an
+    // `origin` index is carried through the merges, so the final pass GATHERS instead of walking the octree again.
+    const bool keep_knn = cfg->skip_dead_samples && !detail && cfg->calc_normal && !cfg->sampling_only;
+    coarse_z_kernel<<<(unsigned)ceil_div(R * n, 256), 256, 0, stream>>>(R, n, w.near, w.far, w.z,
+                                                                        keep_knn ? w.origin : nullptr);
     NMB_LAUNCH_OK();
 
-    auto eval = [&](const float* zarr, int S, float* sdf_out, float* nabla_out, bool color) -> int {
+    auto eval = [&](const float* zarr, int S, float* sdf_out, float* nabla_out, bool color, int64_t entry0) -> int {
       const int64_t Pn = (int64_t)S * R;
-      KnnOut ko{w.k_ds, w.k_slot, w.k_w, w.k_grad, (int64_t)P * R};
+      const int64_t o = keep_knn ? entry0 * R : 0;   // first position of this pass in the neighbour arrays
+      KnnOut ko{w.k_ds + o, w.k_slot + o, w.k_w + o, w.k_grad + o, (int64_t)P * R};
       PointSrc src{nullptr, ro, w.dirs, zarr, R};
       int rc = launch_knn_distance(g, f->indicator.p, f->w1, src, Pn, ko, stream);
       if (rc) return rc;
@@ -751,15 +768,16 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
     const bool carry_nabla = cfg->calc_normal && !live_path && !cfg->sampling_only;
     float* nab_pts = carry_nabla ? w.nabla_pts : nullptr;
     float* nab_new = carry_nabla ? w.nabla_mid : nullptr;   // free until the mid-point pass
-    int rc = eval(w.z, n, w.sdf, nab_pts, false);
+    int rc = eval(w.z, n, w.sdf, nab_pts, false, 0);
     if (rc) return rc;
     for (int it = 0; it < n_iters; ++it) {
       upsample_kernel<<<rb, RT, 0, stream>>>(R, n, n_new, 256.0f * (float)(1 << it), w.z, w.sdf, w.wbuf, w.znew,
                                              cfg->perturb_u ? cfg->perturb_u + (int64_t)it * n_new * N : nullptr, N, perm);
       NMB_LAUNCH_OK();
-      rc = eval(w.znew, n_new, w.sdfnew, nab_new, false);
+      rc = eval(w.znew, n_new, w.sdfnew, nab_new, false, n);
       if (rc) return rc;
-      merge_kernel<<<rb, RT, 0, stream>>>(R, n, n_new, w.z, w.sdf, w.znew, w.sdfnew, nab_pts, nab_new, PR);
+      merge_kernel<<<rb, RT, 0, stream>>>(R, n, n_new, w.z, w.sdf, w.znew, w.sdfnew, nab_pts, nab_new, PR,
+                                          keep_knn ? w.origin : nullptr, n);
       NMB_LAUNCH_OK();
       n += n_new;
     }
@@ -800,8 +818,22 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
       const int64_t M = (int64_t)last_off + last_n;
       if (M > 0) {
         compact_live_kernel<<<rb, RT, 0, stream>>>(R, P, w.live_off, w.wbuf, w.z, w.zmid, w.orig, w.dirs, w.live_mid,
-                                                   w.live_dir, cfg->calc_normal ? w.live_pt : nullptr);
+                                                   w.live_dir, nullptr, keep_knn ? w.origin : nullptr,
+                                                   keep_knn ? w.live_src : nullptr);
         NMB_LAUNCH_OK();
+        if (cfg->calc_normal) {
+          // sdf' * grad ds at the live sample POINTS, from the neighbours the sampling passes found (no second walk);
+          // must run before the mid-point pass below re-uses the neighbour arrays
+          FieldIn in{};
+          in.ds = w.k_ds;
+          in.slot = w.k_slot;
+          in.w = w.k_w;
+          in.grad = w.k_grad;
+          in.stride = PR;
+          in.index = w.live_src;
+          rc = launch_geo(f, in, M, w.sdf_mid, w.nabla_pts, stream);
+          if (rc) return rc;
+        }
         auto eval_list = [&](const float* xyz, float* sdf_out, float* nabla_out, bool color) -> int {
           KnnOut ko{w.k_ds, w.k_slot, w.k_w, w.k_grad, M};
           int rc2;
@@ -830,18 +862,14 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
         };
         rc = eval_list(w.live_mid, w.sdf_mid, need_mid_nabla ? w.nabla_mid : nullptr, true);
         if (rc) return rc;
-        if (cfg->calc_normal) {
-          rc = eval_list(w.live_pt, w.sdf_mid, w.nabla_pts, false);
-          if (rc) return rc;
-        }
       }
       composite_live_kernel<<<rb, RT, 0, stream>>>(R, P, cfg->white_bkgd, w.wbuf, w.zmid, w.live_off, w.rgb, M,
-                                                   cfg->calc_normal ? w.nabla_pts : nullptr, perm, rgb, depth, acc,
+                                                   cfg->calc_normal ? w.nabla_pts : nullptr, PR, perm, rgb, depth, acc,
                                                    normals);
       NMB_LAUNCH_OK();
       continue;
     }
-    rc = eval(w.zmid, P - 1, w.sdf_mid, need_mid_nabla ? w.nabla_mid : nullptr, true);
+    rc = eval(w.zmid, P - 1, w.sdf_mid, need_mid_nabla ? w.nabla_mid : nullptr, true, 0);
     if (rc) return rc;
     composite_kernel<<<rb, RT, 0, stream>>>(R, P, f->s, cfg->white_bkgd, w.sdf, w.zmid, w.rgb, (int64_t)P * R,
                                             cfg->calc_normal ? w.nabla_pts : nullptr, (int64_t)P * R, w.wbuf, perm,
