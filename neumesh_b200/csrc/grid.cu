@@ -554,7 +554,14 @@ knn_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts
     const float qx = __fadd_rn(ox, __fmul_rn(z, dx));
     const float qy = __fadd_rn(oy, __fmul_rn(z, dy));
     const float qz = __fadd_rn(oz, __fmul_rn(z, dz));
-    if (s == s_begin) {
+    if (s == s_begin && s_begin == 0 && src.seed_slot != nullptr) {
+      // warm start from an earlier query of this ray (see PointSrc::seed_slot)
+      const int64_t sp0 = (int64_t)src.seed_entry[r] * src.R + r;
+#pragma unroll
+      for (int k = 0; k < KNN_K; ++k) ix[k] = src.seed_slot[k * src.seed_stride + sp0];
+      warm_rerank<KNN_K>(pts, qx, qy, qz, d2, ix);
+      knn_walk<KNN_K, true, ORDER>(nodes, pts, qx, qy, qz, d2, ix, NMB_GV_ARG(gv));
+    } else if (s == s_begin) {
       knn_walk<KNN_K, false, ORDER>(nodes, pts, qx, qy, qz, d2, ix);
     } else {
       warm_rerank<KNN_K>(pts, qx, qy, qz, d2, ix);

@@ -58,6 +58,12 @@ struct PointSrc {
   const float* rays_d;  // [R,3]
   const float* z;       // [S][R] sample-major depths
   int64_t R;
+  // optional warm start of the FIRST sample of every ray (ray-ordered kernel, segment 0): the 8 neighbour slots of an
+  // earlier query of that ray, stored SoA at seed_slot[k * seed_stride + seed_pos[r]].  Any 8 distinct real points are
+  // a valid warm start (the walk is exact for every starting list), so this only removes a cold walk.
+  const int32_t* seed_slot = nullptr;
+  const int32_t* seed_entry = nullptr;   // [R]: pass entry e of the seed query; its data sits at e * R + r
+  int64_t seed_stride = 0;
 };
 
 // torch.linspace(0, 1, n)[i] in fp32: step * i below the midpoint, fma(-step, n-1-i, 1) above (ATen's CPU kernel)

@@ -727,7 +727,7 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
     // at the end.  Every pass therefore leaves its KNN results in place (pass entry e of ray r at position e * R + r of
     // the SoA arrays: coarse samples are entries 0..N_samples-1, iteration `it` adds N_samples + it * n_new ...) and an
     // `origin` index is carried through the merges, so the final pass GATHERS instead of walking the octree again.
-    const bool keep_knn = cfg->skip_dead_samples && !detail && cfg->calc_normal && !cfg->sampling_only;
+    const bool keep_knn = true;   // (cheap: pointer offsets + one int32 per sample through the merges)
     coarse_z_kernel<<<(unsigned)ceil_div(R * n, 256), 256, 0, stream>>>(R, n, w.near, w.far, w.z,
                                                                         keep_knn ? w.origin : nullptr);
     NMB_LAUNCH_OK();
@@ -737,6 +737,13 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
       const int64_t o = keep_knn ? entry0 * R : 0;   // first position of this pass in the neighbour arrays
       KnnOut ko{w.k_ds + o, w.k_slot + o, w.k_w + o, w.k_grad + o, (int64_t)P * R};
       PointSrc src{nullptr, ro, w.dirs, zarr, R};
+      if (keep_knn && entry0 > 0) {
+        // an up-sampling pass: the first new sample of a ray (u = 0 reproduces the ray's first sample exactly) starts
+        // from the stored neighbours of the ray's current first sample instead of a cold walk
+        src.seed_slot = w.k_slot;
+        src.seed_entry = w.origin;        // row 0 of origin: pass entry of sample 0 of every ray
+        src.seed_stride = (int64_t)P * R;
+      }
       int rc = launch_knn_distance(g, f->indicator.p, f->w1, src, Pn, ko, stream);
       if (rc) return rc;
       FieldIn in{};
@@ -818,8 +825,8 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
       const int64_t M = (int64_t)last_off + last_n;
       if (M > 0) {
         compact_live_kernel<<<rb, RT, 0, stream>>>(R, P, w.live_off, w.wbuf, w.z, w.zmid, w.orig, w.dirs, w.live_mid,
-                                                   w.live_dir, nullptr, keep_knn ? w.origin : nullptr,
-                                                   keep_knn ? w.live_src : nullptr);
+                                                   w.live_dir, nullptr, cfg->calc_normal ? w.origin : nullptr,
+                                                   cfg->calc_normal ? w.live_src : nullptr);
         NMB_LAUNCH_OK();
         if (cfg->calc_normal) {
           // sdf' * grad ds at the live sample POINTS, from the neighbours the sampling passes found (no second walk);
