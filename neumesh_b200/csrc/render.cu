@@ -238,7 +238,10 @@ upsample_kernel(int64_t R, int n, int n_new, float inv_s, const float* __restric
 __global__ void __launch_bounds__(RT)
 merge_kernel(int64_t R, int n, int n_new, float* __restrict__ z, float* __restrict__ sdf,
              const float* __restrict__ znew, const float* __restrict__ sdfnew, float* __restrict__ nab,
-             const float* __restrict__ nabnew, int64_t nstride, int32_t* __restrict__ origin, int origin_new) {
+             const float* __restrict__ nabnew, int64_t nstride, int32_t* __restrict__ origin, int origin_new, int dup0) {
+  // dup0: new sample 0 was NOT evaluated - it is the ray's current first sample again (deterministic up-sampling:
+  // u = 0 returns bins[0] exactly), so its sdf / nabla / origin are copied from sample 0, which is still in place when
+  // new sample 0 is merged (z[0] == znew[0] is never taken before it)
   // origin (nullable): [P][R] index of the evaluation pass entry a sample came from (the KNN results of every pass
   // stay in place: entry e of ray r lives at position e * R + r); new sample b gets origin_new + b
   // nab / nabnew (nullable): [3][nstride] SoA payload (nabla at the samples) carried through the merge
@@ -262,13 +265,14 @@ merge_kernel(int64_t R, int n, int n_new, float* __restrict__ z, float* __restri
       if (a >= 0) za = z[(int64_t)a * R + r];
     } else {
       const int64_t src = (int64_t)b * R + r;
+      const bool copy0 = dup0 && b == 0;
       z[dst] = zb;
-      sdf[dst] = sdfnew[src];
-      if (origin) origin[dst] = origin_new + b;
+      sdf[dst] = copy0 ? sdf[r] : sdfnew[src];
+      if (origin) origin[dst] = copy0 ? origin[r] : origin_new + b;
       if (nab) {
-        nab[dst] = nabnew[src];
-        nab[nstride + dst] = nabnew[nstride + src];
-        nab[2 * nstride + dst] = nabnew[2 * nstride + src];
+        nab[dst] = copy0 ? nab[r] : nabnew[src];
+        nab[nstride + dst] = copy0 ? nab[nstride + r] : nabnew[nstride + src];
+        nab[2 * nstride + dst] = copy0 ? nab[2 * nstride + r] : nabnew[2 * nstride + src];
       }
       --b;
       if (b >= 0) zb = znew[(int64_t)b * R + r];
@@ -781,10 +785,14 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
       upsample_kernel<<<rb, RT, 0, stream>>>(R, n, n_new, 256.0f * (float)(1 << it), w.z, w.sdf, w.wbuf, w.znew,
                                              cfg->perturb_u ? cfg->perturb_u + (int64_t)it * n_new * N : nullptr, N, perm);
       NMB_LAUNCH_OK();
-      rc = eval(w.znew, n_new, w.sdfnew, nab_new, false, n);
+      // deterministic up-sampling: u_0 = 0 returns the ray's first sample again, bit for bit (upsample_kernel: j = 0,
+      // denom -> 1, t = 0) - the same point through the same kernels gives the same sdf, so it is not evaluated twice
+      const int dup0 = (cfg->perturb_u == nullptr && n_new > 1) ? 1 : 0;
+      rc = eval(w.znew + dup0 * R, n_new - dup0, w.sdfnew + dup0 * R, nab_new ? nab_new + dup0 * R : nullptr, false,
+                n + dup0);
       if (rc) return rc;
       merge_kernel<<<rb, RT, 0, stream>>>(R, n, n_new, w.z, w.sdf, w.znew, w.sdfnew, nab_pts, nab_new, PR,
-                                          keep_knn ? w.origin : nullptr, n);
+                                          keep_knn ? w.origin : nullptr, n, dup0);
       NMB_LAUNCH_OK();
       n += n_new;
     }
