@@ -57,50 +57,31 @@ constexpr int A_SLOT16 = 2 * A_HALF16;        // 8 KB
 constexpr int B_HALF16 = MLP_W * SLAB_K * 2;  // 8 KB
 constexpr int B_SLOT16 = 2 * B_HALF16;        // 16 KB
 constexpr float F16_W_SCALE = 256.f;          // weights are packed as 2^8 W (keeps their lo parts out of the subnormals)
-// Two schedules of the fp16x3 engine that were built, validated (all 51 GPU parity tests pass with either) and measured
-// SLOWER on B200 in round 2; both stay compiled out (profiles/r2_mlp_schedule_experiments.txt has the numbers):
-//
-// NMB_TC_PAIR - CTA pairs: the two CTAs of a cluster form one tcgen05 cta_group::2; the leader (cluster rank 0) issues
-// M = 256 MMAs over BOTH CTAs' tiles (rows 0-127 = its own tile, rows 128-255 = the peer's) and each CTA keeps only ITS
-// half of a weight slab (128 of the 256 output columns) in shared memory.  The peer's "MMA warp" is a relay: it waits for
-// the peer's operands / drained accumulator exactly like the leader waits for its own, and forwards each completion to
-// the leader with a remote mbarrier arrive.  Idea: a 128 x 256 x 16 MMA with both operands in shared memory reads 4 KB
-// of A + 8 KB of B and measures ~230 clk instead of the 128 clk of its math; a pair reads 4 + 4 KB per CTA.  Result:
-// ~400 clk per M = 256 MMA, geometry pass 134 ms instead of 88 ms.
-#ifndef NMB_TC_PAIR
-#define NMB_TC_PAIR 0
-#endif
-// NMB_TC_PINGPONG - a CTA works on TWO tiles at a time, accumulator buffer x = tile parity, layer jobs in the order
-// (A,0) (B,0) (A,1) (B,1) ... so that the epilogue of one tile overlaps the MMAs of the other.  A tile's layer l+1
-// overwrites the accumulator of its layer l, so it may only start once the epilogue has drained it completely: the
-// hidden-layer ring then holds a whole layer input (MLP_W / SLAB_K = 16 slabs; a smaller ring deadlocks), which leaves
-// 2 first-layer slots and 3-4 weight slots.  Result: the MMA issuer waits for the builder instead (16 % of its time),
-// the MMAs slow down under the additional shared-memory traffic (690 clk per slab instead of 615): 98 ms instead of 88.
-#ifndef NMB_TC_PINGPONG
-#define NMB_TC_PINGPONG 0
-#endif
-constexpr bool PAIR16 = NMB_TC_PAIR != 0;
-constexpr int XN16 = NMB_TC_PINGPONG ? 2 : 1;
-constexpr int B_SLOT16S = PAIR16 ? B_SLOT16 / 2 : B_SLOT16;   // bytes of a weight slab resident in ONE CTA
-constexpr int B_ROWS16 = PAIR16 ? MLP_W / 2 : MLP_W;         // output columns (rows of the K-major B image) per CTA
-constexpr int NA0_16 = (XN16 == 2 && !PAIR16) ? 2 : 4, NA1_16 = (XN16 == 2) ? MLP_W / SLAB_K : 8, NA_16 = NA0_16 + NA1_16;
-constexpr int nb16(bool sig) { return (XN16 == 2 && !PAIR16) ? (sig ? 3 : 4) : ((XN16 == 2 && sig) ? 4 : 6); }
+// Synchronisation step of the fp16 engine: GR16 = 2 slabs (32 K-columns) share ONE ring slot, i.e. one full / empty
+// barrier pair and one tcgen05.commit pair.  Measured in round 2 (profiles/r2_mlp_schedule_experiments.txt): the single
+// MMA-issuing thread pays ~560 clk of fixed cost per ring step (two barrier polls, tcgen05.fence, descriptors, two
+// commits - one of them cluster-multicast) against ~50 clk per MMA it issues, and that fixed cost - not the tensor core -
+// bounded the engine; one step per 32 columns halves it.  Ring depths below are in steps.
+constexpr int GR16 = 2;
+constexpr int NA0_16 = 2, NA1_16 = 4, NA_16 = NA0_16 + NA1_16, NB_16 = 3;
 
+// SIG: the kernel instantiation exchanges exp(100 z) between value and tangent rows (MODE 1); the others spend those
+// 16 KB on one more first-layer ring step (the MMA thread waits for the builder ~10 % of its time with two)
 template <bool F16, bool SIG = true>
 struct SmemLayoutT {
-  static constexpr int NB_ = F16 ? nb16(SIG) : NB;
+  static constexpr int NA0_ = F16 ? (SIG ? NA0_16 : NA0_16 + 1) : NA0;
   static constexpr int a_off = 0;
-  static constexpr int b_off = F16 ? NA_16 * A_SLOT16 : NA * A_SLOT;
-  static constexpr int sig_off = b_off + (F16 ? NB_ * B_SLOT16S : NB * B_SLOT);   // [group][parity] buffers
-  static constexpr int part_off = sig_off + (SIG ? 4 * SIG_BUF * 4 : 0);   // last-layer partial sums: [3 helpers][3][128]
+  static constexpr int b_off = F16 ? (NA0_ + NA1_16) * GR16 * A_SLOT16 : NA * A_SLOT;
+  static constexpr int sig_off = b_off + (F16 ? NB_16 * GR16 * B_SLOT16 : NB * B_SLOT);   // [group][parity] buffers
+  static constexpr int part_off = sig_off + ((SIG || !F16) ? 4 * SIG_BUF * 4 : 0);   // last-layer partial sums: [3 helpers][3][128]
   static constexpr int const_off = part_off + 9 * ROWS * 4;    // biases + output weights
   static constexpr int bar_off = const_off + CONST_FLOATS * 4;
-  static constexpr int total = bar_off + (F16 ? 1024 : 256);   // mbarriers + the TMEM base address
+  static constexpr int total = bar_off + (F16 ? 512 : 256);   // 2 (NA + NB) + 4 mbarriers + the TMEM base address
 };
 using SmemLayout = SmemLayoutT<false>;
 static_assert(SmemLayoutT<true, true>::total <= 232448 && SmemLayoutT<true, false>::total <= 232448,
               "shared memory budget (fp16 variant)");
-static_assert((2 * (NA_16 + 6) + 4 + 6 + 2) * 8 + 4 <= 1024 && (2 * (NA + NB) + 4) * 8 + 4 <= 256, "mbarrier block");
+static_assert((2 * (NA_16 + 1 + NB_16) + 4) * 8 + 4 <= 512 && (2 * (NA + NB) + 4) * 8 + 4 <= 256, "mbarrier block");
 static_assert(SmemLayout::total <= 232448, "shared memory budget");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -141,30 +122,6 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity)
     if (done) break;
     __nanosleep(40);
   }
-}
-// wait on a LOCAL barrier whose arrivals come from the peer CTA (remote arrive with cluster-scope release)
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    __nanosleep(20);
-  }
-}
-// arrive on the barrier at the same offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
-      "r"(rank)
-      : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -231,23 +188,6 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(IDESC_F16), "r"(accumulate)
-      : "memory");
-}
-// cta_group::2 (CTA pair): M = 256 over both CTAs, each CTA supplies its 128 rows of A and its 128 columns of B
-constexpr uint32_t IDESC_F16_PAIR = (1u << 4) | (0u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
-__device__ __forceinline__ void mma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(IDESC_F16_PAIR), "r"(accumulate)
-      : "memory");
-}
-// completion of the pair's MMAs, signalled on the barrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void mma_commit_pair(uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-      "h"(mask)
       : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
@@ -376,7 +316,6 @@ struct Params {
   int64_t P;
   float* out0;
   float* out1;
-  int exp_flags;
   unsigned long long* dbg;   // optional [8] cycle counters (NMB_TC_PROFILE=1): where the pipeline waits
 };
 
@@ -410,13 +349,10 @@ __global__ void __cluster_dims__(tc::CLUSTER, 1, 1) __launch_bounds__(tc::THREAD
 mlp_tc_kernel(const tc::Params prm) {
   using namespace tc;
   using SmemLayout = SmemLayoutT<F16, MODE == 1>;
-  constexpr int A_HALF = F16 ? A_HALF16 : tc::A_HALF, A_SLOT = F16 ? A_SLOT16 : tc::A_SLOT;
-  constexpr bool PAIR = F16 && PAIR16;   // cta_group::2: see "CTA PAIRS" above
-  constexpr int B_SLOT = F16 ? B_SLOT16S : tc::B_SLOT, B_HALF = B_SLOT / 2;   // per CTA
-  constexpr int B_ROWS = F16 ? B_ROWS16 : MLP_W;
-  constexpr int NA0 = F16 ? NA0_16 : tc::NA0, NA1 = F16 ? NA1_16 : tc::NA1, NA = NA0 + NA1, NB = SmemLayout::NB_;
-  constexpr int XN = F16 ? XN16 : 1;   // tiles in flight per CTA (see "ping-pong" above); every role walks the same job list:
-                                    //   for pair u: for layer l: for x < XN: job (tile iteration u * XN + x, layer l)
+  constexpr int GR = F16 ? GR16 : 1;   // 16-column slabs per ring slot (synchronisation step)
+  constexpr int A_HALF = F16 ? A_HALF16 : tc::A_HALF, A_SUB = F16 ? A_SLOT16 : tc::A_SLOT, A_SLOT = GR * A_SUB;
+  constexpr int B_HALF = F16 ? B_HALF16 : tc::B_HALF, B_SUB = F16 ? B_SLOT16 : tc::B_SLOT, B_SLOT = GR * B_SUB;
+  constexpr int NA0 = SmemLayout::NA0_, NA1 = F16 ? NA1_16 : tc::NA1, NA = NA0 + NA1, NB = F16 ? NB_16 : tc::NB;
   extern __shared__ __align__(1024) char smem[];
   char* a_ring = smem + SmemLayout::a_off;
   char* b_ring = smem + SmemLayout::b_off;
@@ -425,9 +361,8 @@ mlp_tc_kernel(const tc::Params prm) {
   float* cst = reinterpret_cast<float*>(smem + SmemLayout::const_off);   // [n_layers][256] biases, then output rows
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SmemLayout::bar_off);
   // A_FULL / A_EMPTY: slots [0, NA0) belong to the first-layer ring, [NA0, NA) to the hidden-layer ring
-  // PEER_FULL / PEER_DE (pairs, used in the leader): the peer's operands of a slab are in place / its accumulator is drained
   constexpr int A_FULL = 0, A_EMPTY = NA, B_FULL = 2 * NA, B_EMPTY = 2 * NA + NB, D_FULL = 2 * NA + 2 * NB,
-                D_EMPTY = D_FULL + 2, PEER_FULL = D_EMPTY + 2, PEER_DE = PEER_FULL + NB, N_BARS = PEER_DE + 2;
+                D_EMPTY = D_FULL + 2, N_BARS = D_EMPTY + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + N_BARS);
   const uint32_t bar0 = smem_u32(bars);
   auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -439,27 +374,23 @@ mlp_tc_kernel(const tc::Params prm) {
   const int64_t n_tiles_real = (prm.P + PTS - 1) / PTS;
   // every CTA runs the SAME number of tiles (padding with all-invalid tiles): the CTAs of a cluster consume the
   // weight-slab stream in lock step, so none may stop early
-  const int64_t tiles_per_cta = (((n_tiles_real + gridDim.x - 1) / gridDim.x + XN - 1) / XN) * XN;
-  const int64_t n_tiles = tiles_per_cta * gridDim.x;
-  const int64_t n_groups = tiles_per_cta / XN;
+  const int64_t n_tiles = ((n_tiles_real + gridDim.x - 1) / gridDim.x) * gridDim.x;
   const FieldLayout& L = prm.lay;
   const int NL = prm.n_layers;
 
   if (tid == 0) {
     for (int i = 0; i < NA; ++i) {
-      mbar_init(bar(A_FULL + i), 256);   // two half-row producers per row (builders for slots < NA0, epilogue otherwise)
+      // two half-row producers per row and slab (builders for slots < NA0, epilogue otherwise)
+      mbar_init(bar(A_FULL + i), 256 * GR);
       mbar_init(bar(A_EMPTY + i), 1);
     }
     for (int i = 0; i < NB; ++i) {
       mbar_init(bar(B_FULL + i), 1);
-      // released by the MMA warps of every CTA in the cluster (multicast slabs) / by the pair's one commit
-      mbar_init(bar(B_EMPTY + i), PAIR ? 1 : CLUSTER);
-      mbar_init(bar(PEER_FULL + i), 1);
+      mbar_init(bar(B_EMPTY + i), CLUSTER);   // released by the MMA warps of every CTA in the cluster
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(D_FULL + i), 1);
       mbar_init(bar(D_EMPTY + i), N_EPI);
-      mbar_init(bar(PEER_DE + i), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -469,17 +400,10 @@ mlp_tc_kernel(const tc::Params prm) {
     for (int i = tid; i < n_out * MLP_W; i += THREADS) cst[prm.n_layers * MLP_W + i] = prm.w_out[i];
   }
   if (warp == WARP_MMA) {
-    if constexpr (PAIR) {   // the same warp of both CTAs, same destination offset
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                   "r"(512u)
-                   : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
-                   "r"(512u)
-                   : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   cluster_sync_all();   // barriers of every CTA in the cluster are initialised before any multicast can reach them
@@ -493,20 +417,19 @@ mlp_tc_kernel(const tc::Params prm) {
     const int r = (warp & 3) * 32 + (tid & 31);            // row == TMEM lane
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     float* sig_g = sig + grp * 2 * SIG_BUF;
-    uint32_t g = 0;                            // global job counter of this CTA (accumulator buffer = g & 1)
+    uint32_t g = 0;                            // global layer counter of this CTA
+    uint32_t it = 0;                           // tile iteration of this CTA
     const bool prof = prm.dbg != nullptr;
     unsigned long long t_dfull = 0, t_aempty = 0;
     const long long t_begin = clock64();
     constexpr float K_EXP = 144.26950408889634f;       // 100 * log2(e)
     constexpr float K_LOG = 0.0069314718055994531f;    // ln(2) / 100
-    for (int64_t u = 0; u < n_groups; ++u) {
-      for (int l = 0; l < NL; ++l) {
-       for (int x = 0; x < XN; ++x, ++g) {
-        const int64_t tile = blockIdx.x + (u * XN + x) * (int64_t)gridDim.x;
-        const int64_t p = tile * PTS + ((MODE == 1) ? (r & 63) : r);
-        const bool valid = p < prm.P;
-        // hidden-layer ring counter: the K-slabs this job produces, in the order the MMA jobs consume them
-        const uint32_t q = (uint32_t)(((u * (NL - 1) + l) * XN + x) * N_CHUNK);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int64_t p = tile * PTS + ((MODE == 1) ? (r & 63) : r);
+      const bool valid = p < prm.P;
+      // hidden-layer ring counter: slabs of layers 1..NL-1 of all tiles of this CTA, in MMA order
+      uint32_t q = it * (uint32_t)(prm.slabs_per_tile - prm.n_slabs[0]);
+      for (int l = 0; l < NL; ++l, ++g) {
         const uint32_t buf = g & 1u;
         mbar_wait_t(bar(D_FULL + buf), (g >> 1) & 1u, prof, t_dfull);
         tc_fence_after();
@@ -570,11 +493,13 @@ mlp_tc_kernel(const tc::Params prm) {
             }
           }
           if (!last) {
-            const uint32_t qs = q + (uint32_t)j;
-            const uint32_t slot = NA0 + qs % NA1;
-            mbar_wait_t(bar(A_EMPTY + slot), ((qs / NA1) & 1u) ^ 1u, prof, t_aempty);
-            if constexpr (F16) store_a_half_f16(a_ring + slot * A_SLOT, r, hh, v);
-            else store_a_half(a_ring + slot * A_SLOT, r, hh, v);
+            const uint32_t qs = q + (uint32_t)j;          // slab counter; GR consecutive slabs share a ring slot
+            const uint32_t gq = qs / GR;
+            const uint32_t slot = NA0 + gq % NA1;
+            char* a_dst = a_ring + slot * A_SLOT + (qs % GR) * A_SUB;
+            mbar_wait_t(bar(A_EMPTY + slot), ((gq / NA1) & 1u) ^ 1u, prof, t_aempty);
+            if constexpr (F16) store_a_half_f16(a_dst, r, hh, v);
+            else store_a_half(a_dst, r, hh, v);
             fence_proxy_async();
             mbar_arrive(bar(A_FULL + slot));
           } else {
@@ -591,7 +516,9 @@ mlp_tc_kernel(const tc::Params prm) {
         }
         tc_fence_before();
         mbar_arrive(bar(D_EMPTY + buf));
-        if (last) {
+        if (!last) {
+          q += N_CHUNK;
+        } else {
           // combine the four partial dot products of a row (helpers -> smem -> warp-group (grp 0, hh 0))
           const int helper = grp + 2 * hh;   // 0 = finaliser, 1..3 = helpers
           if (helper != 0) {
@@ -631,7 +558,6 @@ mlp_tc_kernel(const tc::Params prm) {
           // helpers may only overwrite `part` after the finaliser has read it
           asm volatile("bar.sync 4, 512;" ::: "memory");
         }
-       }
       }
     }
     if (prof && (tid & 31) == 0) {
@@ -658,10 +584,12 @@ mlp_tc_kernel(const tc::Params prm) {
       const bool tangent = (MODE == 1) && (r >= 64);
       uint32_t q = it * (uint32_t)prm.n_slabs[0];   // first-layer ring counter
       auto emit = [&](const float (&v)[8]) {
-        const uint32_t slot = q % NA0;
-        mbar_wait(bar(A_EMPTY + slot), ((q / NA0) & 1u) ^ 1u);
-        if constexpr (F16) store_a_half_f16(a_ring + slot * A_SLOT, r, h, v);
-        else store_a_half(a_ring + slot * A_SLOT, r, h, v);
+        const uint32_t gq = q / GR;                  // q counts slabs; GR consecutive slabs share a ring slot
+        const uint32_t slot = gq % NA0;
+        char* a_dst = a_ring + slot * A_SLOT + (q % GR) * A_SUB;
+        if (q % GR == 0) mbar_wait(bar(A_EMPTY + slot), ((gq / NA0) & 1u) ^ 1u);
+        if constexpr (F16) store_a_half_f16(a_dst, r, h, v);
+        else store_a_half(a_dst, r, h, v);
         fence_proxy_async();
         mbar_arrive(bar(A_FULL + slot));
         ++q;
@@ -752,6 +680,10 @@ mlp_tc_kernel(const tc::Params prm) {
           fr *= 2.f;
         }
       }
+      if constexpr (GR > 1) {   // the first layer is padded with zero slabs (zero weights) to a whole number of ring steps
+        const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        while (q < (it + 1u) * (uint32_t)prm.n_slabs[0]) emit(zero);
+      }
     }
   } else if (warp == WARP_MMA) {
     // =========================================== MMA issuer =========================================
@@ -761,21 +693,14 @@ mlp_tc_kernel(const tc::Params prm) {
       const bool prof = prm.dbg != nullptr;
       unsigned long long t_dempty = 0, t_a0 = 0, t_a1 = 0, t_b = 0;
       const long long t_begin = clock64();
-      const bool leader = !PAIR || cluster_ctarank() == 0;
-      constexpr uint16_t ALL = (uint16_t)((1u << CLUSTER) - 1u);
-      for (int64_t u = 0; u < n_groups; ++u) {
-        for (int lx = 0; lx < NL * XN; ++lx, ++g) {
-          const int l = lx / XN;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < NL; ++l, ++g) {
           const uint32_t buf = g & 1u;
           mbar_wait_bt(bar(D_EMPTY + buf), ((g >> 1) & 1u) ^ 1u, prof, t_dempty);
-          if constexpr (PAIR) {
-            if (leader) mbar_wait_cluster(bar(PEER_DE + buf), (g >> 1) & 1u);
-            else mbar_arrive_remote(bar(PEER_DE + buf), 0);
-          }
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * 256u;
           const int ns = prm.n_slabs[l];
-          for (int j = 0; j < ns; ++j, ++q) {
+          for (int j = 0; j < ns; j += GR, ++q) {   // q, q0, q1 count ring steps of GR slabs
             uint32_t sa, pa;
             if (l == 0) {
               sa = q0 % NA0;
@@ -789,33 +714,19 @@ mlp_tc_kernel(const tc::Params prm) {
             const uint32_t sb = q % NB;
             mbar_wait_bt(bar(A_FULL + sa), pa, prof, l == 0 ? t_a0 : t_a1);
             mbar_wait_bt(bar(B_FULL + sb), (q / NB) & 1u, prof, t_b);
-            if constexpr (PAIR) {
-              if (!leader) {   // relay: this CTA's half of slab q is complete
-                mbar_arrive_remote(bar(PEER_FULL + sb), 0);
-                continue;
-              }
-              mbar_wait_cluster(bar(PEER_FULL + sb), (q / NB) & 1u);
-            }
             tc_fence_after();
             const uint32_t a_addr = a0 + sa * A_SLOT, b_addr = b0 + sb * B_SLOT;
             if constexpr (F16) {
-              // one K = 16 step per slab: two 8-column chunks; chunk stride: A 128 rows * 16 B, B B_ROWS rows * 16 B
-              const uint64_t a_hi = make_desc(a_addr, ROWS * 16, 128);
-              const uint64_t a_lo = make_desc(a_addr + A_HALF, ROWS * 16, 128);
-              const uint64_t b_hi = make_desc(b_addr, B_ROWS * 16, 128);
-              const uint64_t b_lo = make_desc(b_addr + B_HALF, B_ROWS * 16, 128);
-              if constexpr (PAIR) {
-                mma_f16_pair(d_tmem, a_lo, b_hi, j ? 1u : 0u);   // small terms first
-                mma_f16_pair(d_tmem, a_hi, b_lo, 1u);
-                mma_f16_pair(d_tmem, a_hi, b_hi, 1u);
-              } else {
-                if (!(prm.exp_flags & 1)) {
-                  mma_f16(d_tmem, a_lo, b_hi, j ? 1u : 0u);   // small terms first
-                  mma_f16(d_tmem, a_hi, b_lo, 1u);
-                  mma_f16(d_tmem, a_hi, b_hi, 1u);
-                } else {
-                  mma_f16(d_tmem, a_hi, b_hi, j ? 1u : 0u);
-                }
+#pragma unroll
+              for (int sub = 0; sub < GR; ++sub) {
+                // one K = 16 step per slab: two 8-column chunks; chunk stride: A 128 rows * 16 B, B 256 rows * 16 B
+                const uint64_t a_hi = make_desc(a_addr + sub * A_SUB, ROWS * 16, 128);
+                const uint64_t a_lo = make_desc(a_addr + sub * A_SUB + A_HALF, ROWS * 16, 128);
+                const uint64_t b_hi = make_desc(b_addr + sub * B_SUB, MLP_W * 16, 128);
+                const uint64_t b_lo = make_desc(b_addr + sub * B_SUB + B_HALF, MLP_W * 16, 128);
+                mma_f16(d_tmem, a_lo, b_hi, (j | sub) ? 1u : 0u);   // small terms first
+                mma_f16(d_tmem, a_hi, b_lo, 1u);
+                mma_f16(d_tmem, a_hi, b_hi, 1u);
               }
             } else {
 #pragma unroll
@@ -830,19 +741,10 @@ mlp_tc_kernel(const tc::Params prm) {
                 mma_tf32(d_tmem, a_hi, b_hi, 1u);
               }
             }
-            if constexpr (PAIR) {
-              mma_commit_pair(bar(A_EMPTY + sa), ALL);
-              mma_commit_pair(bar(B_EMPTY + sb), ALL);
-            } else {
-              mma_commit(bar(A_EMPTY + sa));
-              mma_commit_mc(bar(B_EMPTY + sb), ALL);
-            }
+            mma_commit(bar(A_EMPTY + sa));
+            mma_commit_mc(bar(B_EMPTY + sb), (uint16_t)((1u << CLUSTER) - 1u));
           }
-          if constexpr (PAIR) {
-            if (leader) mma_commit_pair(bar(D_FULL + buf), ALL);
-          } else {
-            mma_commit(bar(D_FULL + buf));
-          }
+          mma_commit(bar(D_FULL + buf));
         }
       }
       if (prof) {
@@ -859,23 +761,17 @@ mlp_tc_kernel(const tc::Params prm) {
       uint32_t q = 0;
       const uint32_t b0 = smem_u32(b_ring);
       const uint32_t crank = cluster_ctarank();
-      for (int64_t u = 0; u < n_groups; ++u) {
-        for (int lx = 0; lx < NL * XN; ++lx) {
-          const int l = lx / XN;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < NL; ++l) {
           const float* src = prm.w + prm.slab_off[l];
-          for (int j = 0; j < prm.n_slabs[l]; ++j, ++q) {
+          for (int j = 0; j < prm.n_slabs[l]; j += GR, ++q) {   // GR consecutive slabs are contiguous in the image
             const uint32_t sb = q % NB;
             mbar_wait_backoff(bar(B_EMPTY + sb), ((q / NB) & 1u) ^ 1u);
             mbar_expect_tx(bar(B_FULL + sb), B_SLOT);
-            if constexpr (PAIR) {
-              // this CTA's half of the slab (its 128 output columns: [hi | lo] images, contiguous - pack_tc16_kernel)
-              bulk_load(b0 + sb * B_SLOT, src + ((int64_t)j * CLUSTER + crank) * (B_SLOT / 4), B_SLOT, bar(B_FULL + sb));
-            } else {
-              // this CTA fetches 1/CLUSTER of the slab from L2 and multicasts it to every CTA of the cluster
-              constexpr uint32_t PART = B_SLOT / CLUSTER;
-              bulk_load_mc(b0 + sb * B_SLOT + crank * PART, src + (int64_t)j * (B_SLOT / 4) + crank * (PART / 4), PART,
-                           bar(B_FULL + sb), (uint16_t)((1u << CLUSTER) - 1u));
-            }
+            // this CTA fetches 1/CLUSTER of the slab from L2 and multicasts it to every CTA of the cluster
+            constexpr uint32_t PART = B_SLOT / CLUSTER;
+            bulk_load_mc(b0 + sb * B_SLOT + crank * PART, src + (int64_t)j * (B_SUB / 4) + crank * (PART / 4), PART,
+                         bar(B_FULL + sb), (uint16_t)((1u << CLUSTER) - 1u));
           }
         }
       }
@@ -885,11 +781,7 @@ mlp_tc_kernel(const tc::Params prm) {
   tc_fence_before();
   cluster_sync_all();   // no CTA leaves while a peer may still multicast into its shared memory / barriers
   if (warp == WARP_MMA) {
-    if constexpr (PAIR) {
-      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    } else {
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -926,12 +818,10 @@ __global__ void pack_tc16_kernel(const float* __restrict__ wt /*[K_src][256]*/, 
   const __half hi = __float2half_rn(x);
   const __half lo = __float2half_rn(x - __half2float(hi));
   const int slab = k / tc::SLAB_K, kk = k % tc::SLAB_K;
-  // per slab: [CTA half c (pairs only)][hi | lo][k / 8][row = output column within the half][k % 8]
-  constexpr int RW = tc::B_ROWS16;
-  __half* base = reinterpret_cast<__half*>(dst + (int64_t)slab * (tc::B_SLOT16 / 4)) + (n / RW) * (tc::B_SLOT16S / 2);
-  const int off = (kk / 8) * (RW * 8) + (n % RW) * 8 + (kk % 8);
+  __half* base = reinterpret_cast<__half*>(dst + (int64_t)slab * (tc::B_SLOT16 / 4));
+  const int off = (kk / 8) * (MLP_W * 8) + n * 8 + (kk % 8);
   base[off] = hi;
-  base[tc::B_SLOT16S / 4 + off] = lo;
+  base[tc::B_HALF16 / 2 + off] = lo;
 }
 
 // TC first-layer column k -> FFMA first-layer column (both in "our" orders; see FieldLayout).
@@ -967,11 +857,13 @@ static int pack_one(const MlpFfma& src, const FieldLayout& L, bool color, bool f
   const int slot_floats = (f16 ? tc::B_SLOT16 : tc::B_SLOT) / 4;
   for (int l = 0; l < src.n_layers; ++l) {
     dst->n_slabs[l] = src.K[l] / tc::SLAB_K;
+    if (f16) dst->n_slabs[l] = (int)align_up((int64_t)dst->n_slabs[l], (int64_t)tc::GR16);   // whole ring steps (zero slabs)
     dst->slab_off[l] = total;
     total += (int64_t)dst->n_slabs[l] * slot_floats;
     dst->total_slabs += dst->n_slabs[l];
   }
   NMB_CUDA_OK(dst->w.alloc(total));
+  NMB_CUDA_OK(cudaMemsetAsync(dst->w.p, 0, (size_t)total * sizeof(float), stream));   // padding slabs stay zero
   for (int l = 0; l < src.n_layers; ++l) {
     std::vector<int32_t> kmap;
     if (l == 0) {
@@ -1029,7 +921,6 @@ static int launch_tc(const nmb_field* f, const MlpFfma& fm, const MlpTc& tm, con
   prm.out0 = out0;
   prm.out1 = out1;
   prm.dbg = nullptr;
-  { const char* e = getenv("NMB_TC_EXP"); prm.exp_flags = e ? atoi(e) : 0; }
   static const bool want_prof = getenv("NMB_TC_PROFILE") != nullptr;
   unsigned long long* dbg_dev = nullptr;   // diagnostics only: allocated per launch, the launch is synchronous then
   if (want_prof) {
