@@ -1000,6 +1000,98 @@ bound_rays_kernel(const float4* __restrict__ nodes, const float4* __restrict__ p
   }
 }
 
+// Two-ended variant of the ray-ordered scan (the default for frame-sized batches): only the FIRST and the LAST hit of
+// a ray matter, so the front-to-back search and the back-to-front search are separate launches that talk to each other
+// through bnear / bfar:
+//   launch 1 (BACKWARD = false): thread (segment g ascending, ray r) looks for the first hit of its segment, but gives
+//     up as soon as bnear[r] shows a hit in front of the sample it is about to evaluate;
+//   launch 2 (BACKWARD = true):  thread (segment g DESCENDING, ray r) looks for the last hit of its segment between the
+//     segment's end and the ray's first hit (final after launch 1), and gives up when bfar[r] shows a hit behind it.
+// Blocks are scheduled in grid order, so by the time a segment starts the segments that make it redundant have usually
+// finished; a stale read only costs work, never correctness (bnear / bfar only move towards their final values, and a
+// thread only skips samples that provably cannot change them).  Rays that cross the object evaluate the two OUTER
+// crossings of the 0.1 shell only - not the inner boundary of the shell (ds rises above 0.1 again deep inside the
+// object) - and rays without any hit are scanned once, not twice.  Depths are taken to be non-decreasing along a ray,
+// as in bound_rays_kernel.
+template <bool BACKWARD>
+__global__ void __launch_bounds__(128)
+bound_dir_kernel(const float4* __restrict__ nodes, const float4* __restrict__ pts, const float4* __restrict__ indicator,
+                 float w1, const float* __restrict__ rays_o, const float* __restrict__ dirs,
+                 const float* __restrict__ near, const float* __restrict__ far, int64_t R, int n_grid, float thresh,
+                 int32_t* __restrict__ bnear, int32_t* __restrict__ bfar, ShellGrid shell, const GridView gv) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t r = t % R;
+  const int nseg = (n_grid + BOUND_SEG - 1) / BOUND_SEG;
+  const int gi = (int)(t / R);
+  if (gi >= nseg) return;
+  const int s_begin = (BACKWARD ? nseg - 1 - gi : gi) * BOUND_SEG;
+  const int s_end = min(s_begin + BOUND_SEG, n_grid);
+  const float nr = near[r], fr = far[r];
+  auto depth_at = [&](int s) {
+    const float tt = linspace01(s, n_grid);
+    return __fadd_rn(__fmul_rn(nr, __fsub_rn(1.0f, tt)), __fmul_rn(fr, tt));  // renderer.py:81
+  };
+  // depths are >= 0, so their bit patterns order like the values (bnear starts at +inf, bfar at -1)
+  int32_t first_bits = 0;
+  if (BACKWARD) {
+    first_bits = bnear[r];
+    if (first_bits == 0x7f800000) return;                               // the ray has no hit at all
+    if (__float_as_int(depth_at(s_end - 1)) < first_bits) return;      // the whole segment lies in front of the first hit
+    if (__ldcg(bfar + r) >= __float_as_int(depth_at(s_end - 1))) return;   // a hit behind this segment is known
+  } else {
+    if (__ldcg(bnear + r) < __float_as_int(depth_at(s_begin))) return;   // a hit in front of this segment is known
+  }
+  const float ox = rays_o[r * 3 + 0], oy = rays_o[r * 3 + 1], oz = rays_o[r * 3 + 2];
+  const float dx = dirs[r * 3 + 0], dy = dirs[r * 3 + 1], dz = dirs[r * 3 + 2];
+  float d2[KNN_K];
+  int32_t ix[KNN_K];
+  bool have_prev = false;   // d2 / ix hold the neighbours of some earlier sample of this ray (valid warm start)
+  for (int i = 0; i < s_end - s_begin; ++i) {
+    const int s = BACKWARD ? s_end - 1 - i : s_begin + i;
+    const float depth = depth_at(s);
+    const int32_t dbits = __float_as_int(depth);
+    if (BACKWARD && dbits <= first_bits) {   // reached the first hit: it is the last one as well, as far as this thread knows
+      atomicMax(&bfar[r], first_bits);
+      return;
+    }
+    const float qx = __fadd_rn(ox, __fmul_rn(depth, dx));
+    const float qy = __fadd_rn(oy, __fmul_rn(depth, dy));
+    const float qz = __fadd_rn(oz, __fmul_rn(depth, dz));
+    int code = 0;   // 1: proven outside the shell (mask false), 2: proven inside (mask true), 0: evaluate
+    if (shell.cells) {
+      const float sc = 0.5f * (float)shell.G / shell.B;
+      const float fx = (qx + shell.B) * sc, fy = (qy + shell.B) * sc, fz = (qz + shell.B) * sc;
+      if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)shell.G && fy < (float)shell.G && fz < (float)shell.G) {
+        code = __ldg(shell.cells + ((int64_t)(int)fz * shell.G + (int)fy) * shell.G + (int)fx);
+      } else {
+        const float ex = qx - shell.cx, ey = qy - shell.cy, ez = qz - shell.cz;
+        if (ex * ex + ey * ey + ez * ez >= shell.far_r * shell.far_r) code = 1;
+      }
+    }
+    if (code == 1) continue;
+    bool hit = (code == 2);
+    if (!hit) {
+      // about to walk the octree: worth a look at what the other segments of this ray have found meanwhile
+      if (BACKWARD ? (__ldcg(bfar + r) >= dbits) : (__ldcg(bnear + r) < dbits)) return;
+      if (have_prev) {
+        warm_rerank<KNN_K>(pts, qx, qy, qz, d2, ix);
+        knn_walk<KNN_K, true>(nodes, pts, qx, qy, qz, d2, ix, NMB_GV_ARG(gv));
+      } else {
+        knn_walk<KNN_K, false>(nodes, pts, qx, qy, qz, d2, ix);
+        have_prev = true;
+      }
+      float w[KNN_K], ds, grad[3];
+      mesh_distance_point(pts, indicator, w1, qx, qy, qz, d2, ix, w, ds, grad);
+      hit = ds < thresh;
+    }
+    if (hit) {
+      if (BACKWARD) atomicMax(&bfar[r], dbits);
+      else atomicMin(&bnear[r], dbits);
+      return;
+    }
+  }
+}
+
 int launch_bound_scan(const nmb_grid* g, const float4* indicator, float w1, const float* rays_o, const float* dirs,
                       const float* near, const float* far, int64_t R, int n_grid, float thresh, int32_t* bnear,
                       int32_t* bfar, ShellGrid shell, cudaStream_t stream) {
@@ -1015,6 +1107,18 @@ int launch_bound_scan(const nmb_grid* g, const float4* indicator, float w1, cons
       NMB_COOP_LAUNCH(bound_scan_coop_kernel, ceil_div(n, coop::GROUPS_PER_BLOCK), stream, make_view(g), indicator, w1,
                       rays_o, dirs, near, far, R, n_grid, thresh, bnear, bfar);
     }
+    NMB_LAUNCH_OK();
+    return 0;
+  }
+  static const bool two_ended = getenv("NMB_BOUND_ONE_PASS") == nullptr;
+  if (R >= RAY_KERNEL_MIN_RAYS && two_ended) {
+    const int64_t nseg = ceil_div(n_grid, BOUND_SEG);
+    const ShellGrid sg = (thresh == 0.1f) ? shell : ShellGrid{};
+    bound_dir_kernel<false><<<(unsigned)ceil_div(R * nseg, 128), 128, 0, stream>>>(
+        g->nodes.p, g->pts.p, indicator, w1, rays_o, dirs, near, far, R, n_grid, thresh, bnear, bfar, sg, make_view(g));
+    NMB_LAUNCH_OK();
+    bound_dir_kernel<true><<<(unsigned)ceil_div(R * nseg, 128), 128, 0, stream>>>(
+        g->nodes.p, g->pts.p, indicator, w1, rays_o, dirs, near, far, R, n_grid, thresh, bnear, bfar, sg, make_view(g));
     NMB_LAUNCH_OK();
     return 0;
   }
