@@ -442,7 +442,7 @@ def main():
                  "color": "mlp_tc_kernel<2> (colour MLP)", "mlp_tc": "mlp_tc_kernel<0|1|2> (tcgen05 field MLPs, all "
                  "instantiations)", "knn": "knn_rays_kernel (8-NN walk + mesh distance, ray-ordered)",
                  "knn_list": "knn_lists_kernel (8-NN walk + mesh distance, live samples)",
-                 "bound_scan": "bound_rays_kernel (bounded near/far scan)"}
+                 "bound_scan": "bound_dir_kernel<false|true> (bounded near/far: front-to-back + back-to-front scans)"}
 
         def tensor_roofline(k):
             peak = peaks["bf16_tflops_sustained"]
@@ -504,7 +504,7 @@ def main():
             tot_pts = sum(kern[k]["points_per_step"] for k in walk)
             kern["walk"] = {"ms_per_step": tot_ms, "launches_per_step": sum(kern[k]["launches_per_step"] for k in walk),
                             "points_per_step": tot_pts, "gbs_algorithmic": tot_pts * BYTES_KNN / (tot_ms * 1e-3) / 1e9}
-            kname["walk"] = "knn_rays_kernel + knn_lists_kernel + bound_rays_kernel (exact 8-NN octree walks, all)"
+            kname["walk"] = "knn_rays_kernel + knn_lists_kernel + bound_dir_kernel (exact 8-NN octree walks, all)"
             walk = walk + ["walk"]
         roofline = None
         secondary = None

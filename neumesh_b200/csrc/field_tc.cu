@@ -1,18 +1,24 @@
-// tcgen05 MLP engine (mlp_engine = 0): the NeuMesh geometry / colour MLPs on the 5th-generation tensor cores.
+// tcgen05 MLP engines (mlp_engine = 2: fp16x3 split operands, the default; mlp_engine = 0: 3xTF32): the NeuMesh
+// geometry / colour MLPs on the 5th-generation tensor cores.
 //
-// Why 3xTF32.  The sdf feeds sigmoid(s * sdf) with s ~ 50-300 and a discrete re-sampling cascade; single-pass TF32
+// Why split operands.  The sdf feeds sigmoid(s * sdf) with s ~ 50-300 and a discrete re-sampling cascade; single-pass TF32
 // (10-bit mantissa) or BF16 operands miss the 1e-4 / 1e-5 parity bar by 1-3 orders of magnitude, while the split
 // x = hi + lo (both TF32), D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi with fp32 accumulation in TMEM is fp32-accurate
-// (SURVEY.md section 7.3).  Every algorithmic MAC is therefore issued three times: tensor-pipe utilisation is quoted
-// against ISSUED MMAs and the 3x factor is stated wherever a FLOP/s figure appears.
+// (SURVEY.md section 7.3); the fp16 variant (hi = fp16(x), lo = fp16(x - hi), weights pre-scaled by 2^8) is as accurate
+// at twice the MMA rate and half the operand bytes.  Every algorithmic MAC is therefore issued three times: tensor-pipe
+// utilisation is quoted against ISSUED MMAs and the 3x factor is stated wherever a FLOP/s figure appears.
 //
-// One persistent CTA per SM, 128 rows (points) per tile, warp-specialised:
-//   warps 0-3  epilogue : TMEM -> registers (tcgen05.ld), bias + activation, hi/lo split, next layer's A slabs -> smem
-//   warps 4-7  builder  : neighbour gather + blend + positional encoding -> first-layer A slabs
-//   warp  8    MMA      : one elected lane issues tcgen05.mma (kind::tf32, M=128, N=256, K=8), commits to mbarriers
-//   warp  9    loader   : weight slabs L2 -> smem with cp.async.bulk (TMA 1-D bulk copy) + mbarrier complete_tx
+// One persistent CTA per SM (clusters of 2 share every weight slab), 128 rows (points) per tile, warp-specialised:
+//   warps 0-15  epilogue : TMEM -> registers (tcgen05.ld), bias + activation, hi/lo split, next layer's A slabs -> smem;
+//                          quadrant = w & 3 (TMEM lanes), chunk parity = (w >> 2) & 1, column half = w >> 3
+//   warps 16-23 builder  : neighbour gather + blend + positional encoding -> first-layer A slabs (2 threads per row)
+//   warp  24    MMA      : one lane issues tcgen05.mma (M = 128, N = 256; kind::f16 K = 16 or kind::tf32 K = 8) and the
+//                          tcgen05.commit that release ring slots / publish the accumulator
+//   warp  25    loader   : weight slabs L2 -> smem with cp.async.bulk (TMA 1-D bulk copy, cluster multicast) + complete_tx
 // Layer l's 128x256 fp32 accumulator lives in TMEM columns [256*(l&1), +256); while the epilogue drains it 16 columns
 // at a time into K-slabs of layer l+1, the MMA warp is already accumulating layer l+1 into the other half.
+// Schedules that were built and measured slower on B200 (CTA pairs with cta_group::2, two tiles per CTA, shuffle exchange
+// for the tangent rows, packed f32x2 epilogue arithmetic): profiles/r2_mlp_schedule_experiments.txt, DESIGN.md 4.2.
 //
 // Operand layout (no-swizzle, K-major "interleave" canonical layout): a K-slab of 16 columns is stored as
 // [k/4][row][k%4] fp32, i.e. 8x16-byte core matrices with SBO = 128 B (next 8 rows) and LBO = rows*16 B (next 4 k).

@@ -341,6 +341,18 @@ def test_render_teacher_forced(case5, engine):
     r_rgb, r_depth, r_acc, r_n = _teacher_forced(f, o, d, z_all, True, True)
     f64 = helpers.oracle_field(mesh, cfg, sd, torch.float64)
     t_rgb, t_depth, t_acc, t_n = _teacher_forced(f64, o.double(), d.double(), z_all.double(), True, True)
+    # per-sample outputs at the exported depths: every sample's sdf / nabla must be THE field at that depth - including
+    # the first sample of a ray that each deterministic up-sampling iteration draws again (u = 0) and the fused cascade
+    # copies instead of evaluating
+    dn_ = torch.nn.functional.normalize(d, dim=-1)
+    pts_all = o[:, None, :] + z_all[..., None] * dn_[:, None, :]
+    o_sdf, o_nab = f.forward_with_nablas(pts_all)
+    e_sdf_s = (ex["implicit_surface"].cpu() - o_sdf.squeeze(-1)).abs().max().item()
+    e_nab_s = (ex["implicit_nablas"].cpu() - o_nab).abs().max().item()
+    n_dup = int((z_all[:, 1:] == z_all[:, :-1]).sum())
+    print(f"[{engine}] per-sample sdf {e_sdf_s:.3e} nabla {e_nab_s:.3e} at d_all ({n_dup} duplicated depths)")
+    assert n_dup >= 4 * 1600 * 0.9, "deterministic up-sampling re-draws the first sample of every ray"
+    assert e_sdf_s <= 5e-6 and e_nab_s <= 1.5e-4
     acc = ex["mask_volume"].cpu()
     solid = acc >= 0.5
     e_rgb = (rgb.cpu() - r_rgb).abs().max().item()
