@@ -107,6 +107,17 @@ class ClockSampler:
         self.proc = None
         self.lines = []
         self.thread = None
+        self.first = 0
+
+    def wait_ready(self, timeout: float = 3.0):
+        """Block until nvidia-smi has delivered its first sample (its start-up is over) or `timeout` seconds passed."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        """Start of the timed region: samples taken before (while nvidia-smi was starting up) are dropped."""
+        self.first = len(self.lines)
 
     def start(self):
         try:
@@ -129,7 +140,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[self.first:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -336,6 +347,13 @@ def main():
         torch.cuda.synchronize()
 
     with torch.no_grad():
+        # the clock sampler (one long-running `nvidia-smi -lms`) starts BEFORE the warm-up: its start-up (NVML initialisation)
+        # takes driver locks for a few hundred ms and must not fall into the timed region; only samples from the timed
+        # region are reported
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+            sampler.wait_ready()
         for i in range(args.warmup):
             step_resident(i)
         barrier()
@@ -343,12 +361,10 @@ def main():
         # ---------------- timed region: inputs resident in HBM ----------------
         _lib.profile_enable(True)
         _lib.profile_collect()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         launches0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        sampler.mark()
         e0.record()
         for i in range(args.steps):
             out = step_resident(args.warmup + i)

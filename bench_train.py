@@ -136,15 +136,18 @@ def main(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(i)
-    barrier()
+    # started before the warm-up: nvidia-smi's start-up stalls driver calls for a few hundred ms (bench.py)
     sampler = bench.ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_ready()
+    for i in range(args.warmup):
+        step(i)
+    barrier()
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     e0.record()
     losses = []
     for i in range(args.steps):
