@@ -91,7 +91,10 @@ struct DevBuf {
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
+  // (re)allocation; a buffer that already has `count` elements is kept as it is - a field that is re-packed every
+  // training step must not pay cudaFree + cudaMalloc (both synchronise the device) for buffers of unchanged size
   cudaError_t alloc(int64_t count) {
+    if (p && n == count) return cudaSuccess;
     release();
     n = count;
     if (count <= 0) return cudaSuccess;

@@ -103,7 +103,10 @@ static int pack_ffma(const float* const* v, const float* const* g, const float* 
   NMB_CUDA_OK(out->b_out.alloc(n_out));
   std::vector<int32_t> ident(MLP_W);
   for (int i = 0; i < MLP_W; ++i) ident[i] = i;
-  DevBuf<int32_t> cm0, cmi;
+  // the maps live in the field (no allocation and no synchronisation when a field is re-packed); the uploads come from
+  // pageable host memory, i.e. they are staged before cudaMemcpyAsync returns, so the vectors may go out of scope
+  DevBuf<int32_t>& cm0 = out->cm0;
+  DevBuf<int32_t>& cmi = out->cmi;
   NMB_CUDA_OK(cm0.alloc((int64_t)colmap0.size()));
   NMB_CUDA_OK(cmi.alloc(MLP_W));
   NMB_CUDA_OK(cudaMemcpyAsync(cm0.p, colmap0.data(), colmap0.size() * 4, cudaMemcpyHostToDevice, stream));
@@ -122,7 +125,6 @@ static int pack_ffma(const float* const* v, const float* const* g, const float* 
     NMB_LAUNCH_OK();
   }
   NMB_CUDA_OK(cudaMemcpyAsync(out->b_out.p, b[n_layers], n_out * 4, cudaMemcpyDeviceToDevice, stream));
-  NMB_CUDA_OK(cudaStreamSynchronize(stream));  // cm0/cmi go out of scope
   return 0;
 }
 

@@ -27,6 +27,7 @@ struct MlpFfma {            // fp32 engine: W^T per layer, [K][256] row-major (k
   DevBuf<float> b;          // [n_layers][256]
   DevBuf<float> w_out;      // [n_out][256]
   DevBuf<float> b_out;      // [n_out]
+  DevBuf<int32_t> cm0, cmi; // packing only: first-layer column map, identity map (kept: re-packing allocates nothing)
   int64_t w_off[MAX_LAYERS];
   int K[MAX_LAYERS];
   int n_layers = 0, n_out = 0;
@@ -34,6 +35,7 @@ struct MlpFfma {            // fp32 engine: W^T per layer, [K][256] row-major (k
 
 struct MlpTc {              // tcgen05 engine: per layer, per 16-column K-slab: [hi | lo] x [K/4][256][4] tf32 images
   DevBuf<float> w;
+  DevBuf<int32_t> kmap[MAX_LAYERS];   // packing only: source column of every packed K column (kept between re-packs)
   int64_t slab_off[MAX_LAYERS];  // in floats
   int n_slabs[MAX_LAYERS];
   int total_slabs = 0;

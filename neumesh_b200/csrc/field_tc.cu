@@ -879,7 +879,7 @@ static int pack_one(const MlpFfma& src, const FieldLayout& L, bool color, bool f
       kmap.resize(MLP_W);
       for (int i = 0; i < MLP_W; ++i) kmap[i] = i;
     }
-    DevBuf<int32_t> km;
+    DevBuf<int32_t>& km = dst->kmap[l];   // kept in the field; pageable upload = staged before the call returns
     NMB_CUDA_OK(km.alloc((int64_t)kmap.size()));
     NMB_CUDA_OK(cudaMemcpyAsync(km.p, kmap.data(), kmap.size() * 4, cudaMemcpyHostToDevice, stream));
     const int64_t n = (int64_t)src.K[l] * MLP_W;
@@ -891,7 +891,6 @@ static int pack_one(const MlpFfma& src, const FieldLayout& L, bool color, bool f
                                                                     dst->w.p + dst->slab_off[l]);
     }
     NMB_LAUNCH_OK();
-    NMB_CUDA_OK(cudaStreamSynchronize(stream));
   }
   return 0;
 }
