@@ -1,6 +1,4 @@
 mkdir -p gpurun_out
-# 1. launch list of the bench command (every kernel, device time only)
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2f_launches.csv python bench.py --steps 2 --warmup 1 --cpu-rays 0 > gpurun_out/r2f_launch_bench.log 2>&1
 # 2. full captures (reports stay in /tmp: too large to bring back), exported as raw CSV
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:mlp_tc_kernel -c 8 -o /tmp/r2f_mlp python tools/prof_driver.py 200000 tcgen05_f16 > gpurun_out/r2f_ncu_mlp.log 2>&1
 ncu -i /tmp/r2f_mlp.ncu-rep --page raw --csv > gpurun_out/r2f_mlp_raw.csv 2>/dev/null
