@@ -731,17 +731,17 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
     // at the end.  Every pass therefore leaves its KNN results in place (pass entry e of ray r at position e * R + r of
     // the SoA arrays: coarse samples are entries 0..N_samples-1, iteration `it` adds N_samples + it * n_new ...) and an
     // `origin` index is carried through the merges, so the final pass GATHERS instead of walking the octree again.
-    const bool keep_knn = true;   // (cheap: pointer offsets + one int32 per sample through the merges)
+    // (cheap: pointer offsets + one int32 per sample through the merges)
     coarse_z_kernel<<<(unsigned)ceil_div(R * n, 256), 256, 0, stream>>>(R, n, w.near, w.far, w.z,
-                                                                        keep_knn ? w.origin : nullptr);
+                                                                        w.origin);
     NMB_LAUNCH_OK();
 
     auto eval = [&](const float* zarr, int S, float* sdf_out, float* nabla_out, bool color, int64_t entry0) -> int {
       const int64_t Pn = (int64_t)S * R;
-      const int64_t o = keep_knn ? entry0 * R : 0;   // first position of this pass in the neighbour arrays
+      const int64_t o = entry0 * R;   // first position of this pass in the neighbour arrays
       KnnOut ko{w.k_ds + o, w.k_slot + o, w.k_w + o, w.k_grad + o, (int64_t)P * R};
       PointSrc src{nullptr, ro, w.dirs, zarr, R};
-      if (keep_knn && entry0 > 0) {
+      if (entry0 > 0) {
         // an up-sampling pass: the first new sample of a ray (u = 0 reproduces the ray's first sample exactly) starts
         // from the stored neighbours of the ray's current first sample instead of a cold walk
         src.seed_slot = w.k_slot;
@@ -792,7 +792,7 @@ int nmb_render(const nmb_field* f, const nmb_render_cfg* cfg, const float* rays_
                 n + dup0);
       if (rc) return rc;
       merge_kernel<<<rb, RT, 0, stream>>>(R, n, n_new, w.z, w.sdf, w.znew, w.sdfnew, nab_pts, nab_new, PR,
-                                          keep_knn ? w.origin : nullptr, n, dup0);
+                                          w.origin, n, dup0);
       NMB_LAUNCH_OK();
       n += n_new;
     }
