@@ -126,3 +126,32 @@ def test_render_fused_empty_shard_needs_no_library_call():
     assert out["implicit_nablas"].shape == (0, 128, 3) and out["colors"].shape == (0, 127, 3)
     full = parallel.gather_image({k: out[k] for k in ("rgb", "depth_volume", "mask_volume", "normals_volume")}, 0, 0, 1)
     assert full["rgb"].shape == (0, 3)
+
+
+def test_clock_sampler_reports_only_samples_of_the_timed_region():
+    """bench.py starts `nvidia-smi -lms` before the warm-up (its start-up stalls driver calls) and must report only the
+    samples taken after `mark()`: the warm-up clocks and throttle reasons do not describe the timed steps."""
+    import bench
+
+    class _Proc:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+
+    s = bench.ClockSampler(0)
+    s.proc = _Proc()
+    s.lines = ["0, 1200, 1965, 300.0, Not Active, Active, Not Active, Not Active\n"] * 3     # start-up / warm-up
+    s.mark()
+    s.lines += ["0, 1950, 1965, 800.0, Not Active, Not Active, Not Active, Active\n",
+                "0, 1920, 1965, 790.0, Not Active, Not Active, Not Active, Active\n",
+                "garbage line\n"]
+    out = s.stop()
+    assert out["samples"] == 2 and out["sm_mhz"] == 1935.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"]          # the warm-up's hw_thermal_slowdown is not reported
+    # without nvidia-smi the bench still prints a line
+    t = bench.ClockSampler(0)
+    t.wait_ready(0.01)
+    t.mark()
+    assert t.stop()["reasons"] == ["nvidia-smi unavailable"]
